@@ -1,0 +1,172 @@
+/*
+ * yolo1_b200.h -- C ABI of the B200-native YOLO v1 hot path (libyolo1_b200.so).
+ *
+ * The reference (haoran1062/YOLO_V1, pure Python on ATen ops) has no FFI layer of its own; its
+ * boundary for this path is three Python call signatures.  Each entry point below names the reference
+ * interface it replaces (file:line relative to /root/reference); the Python host side in
+ * yolo_v1_b200/ re-creates those signatures on top of this ABI through ctypes, and INTEGRATION.md
+ * shows the stub a maintainer of the reference would add.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; no torch / pybind types.  `stream` is a cudaStream_t passed as
+ *     void* (NULL = the legacy default stream).
+ *   - return 0 on success, < 0 for an invalid argument (no CUDA call was made), > 0 = the cudaError_t
+ *     of the failing CUDA call.  No exceptions, no exit() (unlike utils/utils.py:30-32).
+ *   - device entry points never allocate, never synchronise the host and keep no global state: the
+ *     caller owns every buffer; calls are stream ordered and re-entrant.
+ *   - strides are in ELEMENTS over (image n, row i, column j, channel c).  The backbone hands the loss
+ *     a permuted NCHW view (backbones/OriginResNet.py:189): strides (D*S*S, S, 1, S*S).
+ *   - dtype: 0 = float32, 1 = bfloat16 (pred / grad only; targets and outputs are float32).
+ *   - channel layout of pred and target (v1Loss.py:24-25, utils/YOLODataLoader.py:220-227):
+ *       [conf_0..conf_{B-1}, (x,y,w,h)_0..(x,y,w,h)_{B-1}, cls_0..cls_{C-1}],  D = 5B + C.
+ */
+#ifndef YOLO1_B200_H_
+#define YOLO1_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define YOLO1_API __attribute__((visibility("default")))
+#else
+#define YOLO1_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YOLO1_ABI_VERSION 1
+
+#define YOLO1_DTYPE_F32 0
+#define YOLO1_DTYPE_BF16 1
+
+#define YOLO1_COORD_REFERENCE 0 /* row-slice behaviour of v1Loss.py:101 (first two objects plain, rest sqrt) */
+#define YOLO1_COORD_PAPER 1     /* xy plain, wh sqrt for every object */
+
+#define YOLO1_ERR_ARG (-1)         /* null pointer / negative size / bad enum */
+#define YOLO1_ERR_UNSUPPORTED (-2) /* shape outside what the kernels are built for (see each call) */
+#define YOLO1_ERR_ALIGN (-3)       /* a pointer is not aligned to its element size */
+
+YOLO1_API int yolo1_abi_version(void);
+
+/* Human readable text for a return code of this library (static storage). */
+YOLO1_API const char* yolo1_error_string(int rc);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss: replaces YOLOLossV1.forward (v1Loss.py:22-118) AND its autograd backward (train.py:171) in one
+ * fused pass.  B <= 8, 5B+C <= 128.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Bytes of device scratch `yolo1_loss_fwd_bwd` needs (independent of N; 64 KB + a header; 8-byte aligned). */
+YOLO1_API size_t yolo1_loss_workspace_bytes(int64_t N, int S, int B, int C);
+
+/*
+ * pred [N,S,S,D] (pred_dtype, pred_strides), target [N,S,S,D] float32 (target_strides).
+ * grad  : d total / d pred, same dtype as pred, layout grad_strides (NULL => forward only).
+ * terms : device float[5] = {location, contain, not_contain, classify} each divided by batch_size (the
+ *         four numbers v1Loss.py:108 logs) and the total loss (v1Loss.py:104-105).
+ * inv_batch_size : 1 / _batch_size of the constructor (v1Loss.py:18,105) -- NOT 1/N.
+ * coord_mode : YOLO1_COORD_REFERENCE reproduces v1Loss.py:101 exactly.
+ * The gradient includes the path through the IoU target (v1Loss.py:78 keeps the graph).
+ */
+YOLO1_API int yolo1_loss_fwd_bwd(const void* pred, const int64_t pred_strides[4], int pred_dtype,
+                       const float* target, const int64_t target_strides[4],
+                       void* grad, const int64_t grad_strides[4], float* terms,
+                       int64_t N, int S, int B, int C,
+                       float lambda_coord, float lambda_noobj, float inv_batch_size, int coord_mode,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/*
+ * Tuning / diagnostic twin of yolo1_loss_fwd_bwd: `variant` picks the launch shape of the streaming kernel
+ * (0 = the default yolo1_loss_fwd_bwd uses; 1..7 = other tile-cells x input-stages x output-buffers
+ * shapes, see loss.cu launch_tma_variant; < 0 = force the strided one-thread-per-cell kernel that also
+ * serves non-contiguous views).  Same results for every variant up to summation order.
+ */
+YOLO1_API int yolo1_loss_fwd_bwd_ex(const void* pred, const int64_t pred_strides[4], int pred_dtype,
+                          const float* target, const int64_t target_strides[4],
+                          void* grad, const int64_t grad_strides[4], float* terms,
+                          int64_t N, int S, int B, int C,
+                          float lambda_coord, float lambda_noobj, float inv_batch_size, int coord_mode,
+                          void* workspace, size_t workspace_bytes, int variant, void* stream);
+
+/*
+ * grad *= *grad_out_dev, in place, for autograd's backward(grad_output) (train.py:171 calls
+ * loss.backward() with grad_output = 1; AMP loss scaling makes it != 1).  The kernel reads the scalar
+ * on the device and returns without touching memory when it is exactly 1.0f, so the usual training
+ * step pays one empty launch and no traffic.  `storage_numel` elements starting at grad (the dense
+ * storage of the gradient, any stride order).
+ */
+YOLO1_API int yolo1_scale_grad(void* grad, int dtype, int64_t storage_numel, const float* grad_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decode + NMS: replaces decoder (utils/utils.py:94-147) and nms (utils/utils.py:150-184), batched
+ * over images.  B is the number of boxes per cell, max_n = S*S*B <= 1024 candidates per image.
+ * Arithmetic is bit-exact with the reference's fp32 ATen CPU ops (no FMA contraction).
+ * ---------------------------------------------------------------------------------------------- */
+
+/*
+ * decoder's candidate loop, utils/utils.py:108-132.  Per image n writes the boxes that pass
+ * `conf*maxprob > thresh` in row-major (i,j,b) emission order:
+ *   boxes [N,max_n,4] xyxy (image-normalised), scores [N,max_n], cls [N,max_n], counts [N].
+ * `thresh` is a double because the reference compares in Python double (utils/utils.py:129).
+ */
+YOLO1_API int yolo1_decode(const void* pred, const int64_t pred_strides[4], int pred_dtype,
+                 int64_t N, int S, int B, int C, double thresh,
+                 float* boxes, float* scores, int32_t* cls, int32_t* counts, void* stream);
+
+/*
+ * nms, utils/utils.py:150-184, for N independent box sets of counts[n] <= max_n boxes each
+ * (boxes [N,max_n,4], scores [N,max_n]).  keep [N,max_n] receives indices into the input set in
+ * descending score order (ties: lower index first), keep_counts [N] their number.
+ * per_class = 0 is the reference behaviour (class-agnostic; cls may be NULL); per_class = 1 only lets
+ * boxes of equal cls suppress each other.  A box survives iff ovr <= (float)iou_thr.
+ */
+YOLO1_API int yolo1_nms(const float* boxes, const float* scores, const int32_t* cls, const int32_t* counts,
+              int64_t N, int max_n, float iou_thr, int per_class,
+              int32_t* keep, int32_t* keep_counts, void* stream);
+
+/*
+ * decoder end to end (utils/utils.py:94-147) in one kernel per image; candidates never leave shared
+ * memory.  Outputs, per image, the kept detections in descending score order:
+ *   out_boxes [N,max_n,4], out_scores [N,max_n], out_cls [N,max_n], out_counts [N]
+ *   (out_counts[n] == 0 <=> the reference returns its all-zero sentinel, utils/utils.py:134-137).
+ * Optional (may be NULL): keep_idx [N,max_n] = kept candidate indices in emission order (what nms()
+ * returns), cand_counts [N] = candidates before NMS.
+ */
+YOLO1_API int yolo1_decode_nms(const void* pred, const int64_t pred_strides[4], int pred_dtype,
+                     int64_t N, int S, int B, int C, double thresh, float iou_thr, int per_class,
+                     float* out_boxes, float* out_scores, int32_t* out_cls, int32_t* out_counts,
+                     int32_t* keep_idx, int32_t* cand_counts, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer entry points: the same path for callers that hold HOST memory (the reference's callers
+ * hold CPU tensors when run as shipped with device='cpu').  A context owns the device staging
+ * buffers, the pinned bounce buffers and the copy/compute streams; batches are cut into chunks and
+ * H2D copy, kernel and D2H copy of consecutive chunks overlap.  These calls block until the results
+ * are in the host buffers.  One context per host thread.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct yolo1_host_ctx yolo1_host_ctx;
+
+/* chunk_images: images per pipeline chunk (0 = pick automatically); max S*S*D per image fixed here. */
+YOLO1_API int yolo1_host_ctx_create(yolo1_host_ctx** ctx, int device, int S, int B, int C, int64_t chunk_images);
+YOLO1_API void yolo1_host_ctx_destroy(yolo1_host_ctx* ctx);
+
+/* Register / unregister caller memory as pinned (cudaHostRegister) so the copies run at full PCIe rate. */
+YOLO1_API int yolo1_host_pin(void* ptr, size_t bytes);
+YOLO1_API int yolo1_host_unpin(void* ptr);
+
+/* pred/target/grad: contiguous float32 [N,S,S,D] in host memory; terms: host float[5]. grad may be NULL. */
+YOLO1_API int yolo1_loss_fwd_bwd_host(yolo1_host_ctx* ctx, const float* pred, const float* target, float* grad,
+                            float terms[5], int64_t N, float lambda_coord, float lambda_noobj,
+                            float inv_batch_size, int coord_mode);
+
+/* pred: contiguous float32 [N,S,S,D] in host memory; outputs as yolo1_decode_nms, in host memory. */
+YOLO1_API int yolo1_decode_nms_host(yolo1_host_ctx* ctx, const float* pred, int64_t N, double thresh, float iou_thr,
+                          int per_class, float* out_boxes, float* out_scores, int32_t* out_cls,
+                          int32_t* out_counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YOLO1_B200_H_ */

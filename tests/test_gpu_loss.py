@@ -1,0 +1,261 @@
+"""K1 parity: the fused CUDA loss (through the C ABI / the reference-shaped module) against
+  (1) the golden vectors produced by the reference's own code (tests/golden/loss_cases.npz),
+  (2) the CPU oracle (oracle/yolo1_oracle.c, itself pinned to those vectors) on seeded synthetic inputs,
+  (3) size-independent properties at BASELINE config sizes.
+Tolerance (north_star): loss and gradients within 1e-5 relative in fp32
+  -- loss: |a-b| <= 1e-5 |b|;  gradient: max|a-b| <= 1e-5 max|b|.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+from yolo_v1_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, -1]   # launch shapes of the streaming kernel; -1 = strided kernel
+
+
+def _y():
+    import yolo_v1_b200 as y
+    return y
+
+
+def _check(terms, grad, o_terms, o_grad, what, tol=TOL):
+    terms = terms.detach().float().cpu().numpy()
+    for t in range(5):
+        assert abs(terms[t] - o_terms[t]) <= tol * max(abs(o_terms[t]), 1e-6), (what, "term", t, terms, o_terms)
+    if grad is not None:
+        g = grad.detach().float().cpu().numpy()
+        assert g.shape == o_grad.shape
+        err = np.abs(g - o_grad).max()
+        assert err <= tol * max(np.abs(o_grad).max(), 1e-12), (what, "grad", err, np.abs(o_grad).max())
+
+
+def test_golden_cases_from_the_reference(golden_dir):
+    y = _y()
+    z = np.load(os.path.join(golden_dir, "loss_cases.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    assert len(names) >= 10
+    for name in names:
+        S, B, C, lc, ln, bs = z[name + "/hyper"]
+        pred = torch.from_numpy(z[name + "/pred"]).cuda()
+        target = torch.from_numpy(z[name + "/target"]).cuda()
+        for variant in (0, 6, -1):
+            loss, grad, terms = y.yolo_loss_fused(pred, target, batch_size=float(bs), S=int(S), B=int(B), C=int(C),
+                                                  l_coord=float(lc), l_noobj=float(ln), variant=variant)
+            ref_loss, ref_grad = float(z[name + "/loss"]), z[name + "/grad"]
+            assert abs(float(loss) - ref_loss) <= TOL * max(abs(ref_loss), 1e-12), (name, variant)
+            err = np.abs(grad.cpu().numpy() - ref_grad).max()
+            assert err <= TOL * max(np.abs(ref_grad).max(), 1e-12), (name, variant, err)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("S,N,p_obj,kind", [(7, 67, None, "encoder"), (14, 33, None, "encoder"),
+                                            (7, 40, 0.5, "mixed"), (14, 9, 0.5, "mixed")])
+def test_against_oracle_all_launch_shapes(variant, S, N, p_obj, kind):
+    y = _y()
+    pred, target = synth.make_loss_inputs(N, S, p_obj=p_obj, seed=20241018 + S + N, variant=kind)
+    o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=N)
+    loss, grad, terms = y.yolo_loss_fused(pred.cuda(), target.cuda(), batch_size=N, variant=variant)
+    _check(terms, grad, o_terms, o_grad, (variant, S, N, kind))
+    assert float(loss) == float(terms[4])
+    # forward only (grad = NULL) gives the same terms
+    _, g2, t2 = y.yolo_loss_fused(pred.cuda(), target.cuda(), batch_size=N, variant=variant, want_grad=False)
+    assert g2 is None and torch.equal(t2, terms)
+
+
+@pytest.mark.parametrize("N", [0, 1, 2, 3, 5, 127, 128, 129, 1000])
+def test_ragged_sizes_and_tail_path(N):
+    """N*S*S not a multiple of the tile: the tail cells go through the direct path; N=0 gives zeros."""
+    y = _y()
+    pred, target = synth.make_loss_inputs(N, 7, seed=5 + N, p_obj=0.2)
+    bs = max(N, 1)
+    o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=bs)
+    for variant in (0, 5, 6):
+        _, grad, terms = y.yolo_loss_fused(pred.cuda(), target.cuda(), batch_size=bs, variant=variant)
+        _check(terms, grad, o_terms, o_grad, ("ragged", N, variant))
+
+
+def test_permuted_nchw_view_is_read_in_place():
+    """The backbone hands the loss a permuted NCHW view (OriginResNet.py:189): same numbers, gradient
+    written in the same physical layout, no .contiguous()."""
+    y = _y()
+    pred, target = synth.make_loss_inputs(50, 14, seed=77, p_obj=0.1)
+    o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=50)
+    planar = pred.cuda().permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+    assert not planar.is_contiguous()
+    _, grad, terms = y.yolo_loss_fused(planar, target.cuda(), batch_size=50)
+    assert grad.stride() == planar.stride()
+    _check(terms, grad, o_terms, o_grad, "planar")
+    # an offset (unaligned) slice of a bigger buffer also works (falls to the strided kernel)
+    big = torch.zeros(51 * 14 * 14 * 30 + 1, device="cuda")
+    view = big[1:1 + 50 * 14 * 14 * 30].view(50, 14, 14, 30)
+    view.copy_(pred)
+    _, grad, terms = y.yolo_loss_fused(view, target.cuda(), batch_size=50)
+    _check(terms, grad, o_terms, o_grad, "unaligned")
+
+
+def test_batch_size_divisor_lambdas_and_paper_mode():
+    y = _y()
+    pred, target = synth.make_loss_inputs(16, 7, seed=3, p_obj=0.3, variant="mixed")
+    for bs, lc, ln, mode in [(64, 5.0, 0.5, 0), (16, 2.5, 0.25, 0), (7, 5.0, 0.5, 1)]:
+        o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), l_coord=lc, l_noobj=ln, batch_size=bs, coord_mode=mode)
+        _, grad, terms = y.yolo_loss_fused(pred.cuda(), target.cuda(), batch_size=bs, l_coord=lc, l_noobj=ln,
+                                           coord_mode="paper" if mode else "reference")
+        _check(terms, grad, o_terms, o_grad, (bs, lc, ln, mode))
+
+
+def test_general_B_and_C_use_the_strided_kernel():
+    y = _y()
+    for B, C in [(1, 20), (3, 5), (2, 21), (4, 1)]:
+        pred, target = synth.make_loss_inputs(12, 7, B=B, C=C, seed=B * 100 + C, p_obj=0.3, variant="mixed")
+        o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), B=B, C=C, batch_size=12)
+        _, grad, terms = y.yolo_loss_fused(pred.cuda(), target.cuda(), batch_size=12, B=B, C=C)
+        _check(terms, grad, o_terms, o_grad, (B, C))
+
+
+def test_bf16_pred_and_grad():
+    """bf16 I/O (config 5): math in fp32 on the bf16-rounded values; compare with the oracle fed the same
+    rounded values; the gradient is rounded to bf16 on store (tolerance = bf16 half-ulp, 2^-8 relative)."""
+    y = _y()
+    pred, target = synth.make_loss_inputs(40, 7, seed=11, p_obj=0.2)
+    pb = pred.to(torch.bfloat16)
+    o_terms, o_grad = O.loss(pb.float().numpy(), target.numpy(), batch_size=40)
+    for variant in (0, 6, -1):
+        _, grad, terms = y.yolo_loss_fused(pb.cuda(), target.cuda(), batch_size=40, variant=variant)
+        assert grad.dtype == torch.bfloat16
+        _check(terms, None, o_terms, None, ("bf16", variant))
+        g = grad.float().cpu().numpy()
+        assert np.all(np.abs(g - o_grad) <= np.abs(o_grad) * 2.0 ** -8 + 1e-30), variant
+
+
+def test_module_matches_reference_call_shape_and_autograd():
+    """train.py:101,167,171: lossLayer = YOLOLossV1(bs,S,B,C,lc,ln); loss = lossLayer(pred,target); backward."""
+    y = _y()
+    pred, target = synth.make_loss_inputs(32, 7, seed=20241018)   # BASELINE config 1 shape
+    o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=32)
+    mod = y.YOLOLossV1(32, 7, 2, 20, 5., .5, _device='cuda:0')
+    assert len(list(mod.parameters())) == 0 and len(mod.state_dict()) == 0
+    p = pred.cuda().requires_grad_(True)
+    loss = mod(p, target.cuda())
+    assert loss.dim() == 0 and loss.grad_fn is not None
+    loss.backward()
+    _check(mod.last_terms, p.grad, o_terms, o_grad, "module")
+    # grad_output != 1 (AMP loss scaling): gradient scales, through a sigmoid head like the backbone's
+    z = torch.randn(32, 7, 7, 30, device="cuda", requires_grad=True)
+    out = torch.sigmoid(z)
+    (mod(out, target.cuda()) * 3.0).backward()
+    zc = z.detach().cpu().numpy()
+    sg = 1.0 / (1.0 + np.exp(-zc.astype(np.float64)))
+    _, og = O.loss(sg.astype(np.float32), target.numpy(), batch_size=32)
+    want = 3.0 * og * (sg * (1 - sg))
+    assert np.abs(z.grad.cpu().numpy() - want).max() <= 2e-5 * np.abs(want).max()
+    # no grad requested -> forward only
+    with torch.no_grad():
+        l2 = mod(pred.cuda(), target.cuda())
+    assert abs(float(l2) - float(o_terms[4])) <= TOL * abs(float(o_terms[4]))
+
+
+def test_module_logging_hooks():
+    y = _y()
+    pred, target = synth.make_loss_inputs(4, 7, seed=1, p_obj=0.2)
+
+    class Log:
+        def __init__(self):
+            self.lines = []
+
+        def info(self, s):
+            self.lines.append(s)
+
+    class Vis:
+        def __init__(self):
+            self.calls = []
+
+        def plot(self, name, v):
+            self.calls.append((name, v))
+
+    lg, vis = Log(), Vis()
+    mod = y.YOLOLossV1(4, 7, 2, 20, _logger=lg, _vis=vis)
+    mod(pred.cuda(), target.cuda())
+    o_terms, _ = O.loss(pred.numpy(), target.numpy(), batch_size=4)
+    import re
+    assert len(lg.lines) == 1
+    m = re.fullmatch(r'location loss : (\S+) contain loss : (\S+) not contain loss: (\S+) classify loss : (\S+)',
+                     lg.lines[0])                                   # the format of v1Loss.py:108
+    assert m and np.allclose([float(v) for v in m.groups()], o_terms[:4], atol=2e-5)
+    assert np.allclose([c[1] for c in vis.calls], o_terms[:4], rtol=1e-5)
+    assert [c[0] for c in vis.calls] == ['location loss', 'confidence loss', 'no object loss', 'classify loss']
+
+
+def test_deterministic_and_stream_ordered():
+    y = _y()
+    pred, target = synth.make_loss_inputs(4096, 7, seed=9)
+    p, t = pred.cuda(), target.cuda()
+    _, g1, t1 = y.yolo_loss_fused(p, t, batch_size=4096)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        _, g2, t2 = y.yolo_loss_fused(p, t, batch_size=4096)
+    s.synchronize()
+    assert torch.equal(t1, t2) and torch.equal(g1, g2)
+
+
+def test_host_buffer_path_equals_device_path_and_spans_chunks():
+    """yolo1_loss_fwd_bwd_host: chunked H2D/kernel/D2H pipeline; the `[:2]` rule (v1Loss.py:101) must span
+    chunk boundaries: objects placed so that the call's 1st, 2nd and 3rd objects sit in different chunks."""
+    y = _y()
+    N, S = 23, 7
+    pred, target = synth.make_loss_inputs(N, S, seed=123, p_obj=0.0)
+    g = torch.Generator().manual_seed(4)
+    for (n, i, j) in [(1, 2, 3), (9, 0, 0), (10, 6, 6), (22, 3, 3)]:
+        target[n, i, j, :2] = 1
+        bx = torch.rand(4, generator=g) * 0.8 + 0.1
+        target[n, i, j, 2:6] = bx
+        target[n, i, j, 6:10] = bx
+        target[n, i, j, 10 + (n % 20)] = 1
+    o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=N)
+    for chunk in (0, 4, 1, 23, 100):
+        ctx = y.HostContext(S, chunk_images=chunk)
+        terms, grad = ctx.loss(pred, target, batch_size=N)
+        _check(terms, grad, o_terms, o_grad, ("host", chunk))
+        t2, g2 = ctx.loss(pred.pin_memory(), target.pin_memory(), batch_size=N, want_grad=False)
+        assert g2 is None and torch.equal(t2, terms)
+        ctx.close()
+    # the module accepts CPU tensors too (reference `_device='cpu'` call shape); arithmetic still on the GPU
+    mod = y.YOLOLossV1(N, S, 2, 20, _device='cpu')
+    p = pred.clone().requires_grad_(True)
+    mod(p, target).backward()
+    _check(mod.last_terms, p.grad, o_terms, o_grad, "host module")
+
+
+def test_full_size_properties_config3():
+    """BASELINE config 3 (N=65536, S=14: 12.8 M cells, 1.54 GB per tensor).  The oracle checks a 512-image
+    sub-batch; the rest is covered by properties: the gradient is local (a sub-batch run reproduces the
+    slice bit for bit outside the first two object cells), and the raw sums are additive over a split."""
+    y = _y()
+    N, S = 65536, 14
+    pred, target = synth.make_loss_inputs(N, S, seed=20241018 + 3000, device="cuda")
+    _, grad, terms = y.yolo_loss_fused(pred, target, batch_size=N, coord_mode="paper")
+    # additivity (paper mode has no call-order dependence): halves sum to the whole
+    h = N // 2
+    _, _, ta = y.yolo_loss_fused(pred[:h], target[:h], batch_size=N, coord_mode="paper")
+    _, _, tb = y.yolo_loss_fused(pred[h:], target[h:], batch_size=N, coord_mode="paper")
+    assert torch.allclose(ta + tb, terms, rtol=2e-6, atol=0)
+    # locality + oracle on a sub-batch from the middle
+    a, b = 30000, 30512
+    _, gs, ts = y.yolo_loss_fused(pred[a:b], target[a:b], batch_size=N, coord_mode="paper")
+    assert torch.equal(gs, grad[a:b])
+    o_terms, o_grad = O.loss(pred[a:b].cpu().numpy(), target[a:b].cpu().numpy(), batch_size=N, coord_mode=1)
+    _check(ts, gs, o_terms, o_grad, "config3 sub-batch")
+    # reference mode: identical except the location term / the first two object cells of the call
+    _, gr, tr = y.yolo_loss_fused(pred, target, batch_size=N)
+    diff = (gr != grad).reshape(-1, 30).any(dim=1).nonzero().reshape(-1)
+    objs = (target[..., 0].reshape(-1) == 1).nonzero().reshape(-1)
+    assert diff.numel() == objs.numel()              # paper vs reference differ on every object cell (xy vs sqrt)
+    o_small, og_small = O.loss(pred[:64].cpu().numpy(), target[:64].cpu().numpy(), batch_size=N)
+    assert np.abs(gr[:64].cpu().numpy() - og_small).max() <= TOL * np.abs(og_small).max()
+    assert torch.equal(tr[1:4], terms[1:4])

@@ -1,0 +1,92 @@
+"""CPU-only: host-side logic that needs no GPU -- sharding arithmetic, interface shape of the
+reference-compatible module and functions, input validation, synthetic generators."""
+import inspect
+
+import numpy as np
+import pytest
+import torch
+
+import yolo_v1_b200 as y
+from yolo_v1_b200 import synth
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 8, 9, 1048576, 1048577):
+        for w in (1, 2, 3, 4, 8):
+            spans = [y.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        y.shard_range(10, 4, 4)
+
+
+def test_signatures_match_the_reference_call_sites():
+    """v1Loss.py:10,22 -- utils/utils.py:94,150 (names, order and defaults)."""
+    sig = inspect.signature(y.YOLOLossV1.__init__)
+    names = list(sig.parameters)[1:10]
+    assert names == ['_batch_size', '_S', '_B', '_clsN', '_l_coord', '_l_noobj', '_device', '_logger', '_vis']
+    assert sig.parameters['_l_coord'].default == 5. and sig.parameters['_l_noobj'].default == 0.5
+    assert sig.parameters['_device'].default == 'cuda:0'
+    assert list(inspect.signature(y.YOLOLossV1.forward).parameters) == ['self', 'pred_tensor', 'target_tensor']
+    d = inspect.signature(y.decoder)
+    assert list(d.parameters) == ['pred', 'grid_num', 'B', 'device', 'thresh', 'nms_th', 'gt']
+    assert [d.parameters[k].default for k in list(d.parameters)[1:]] == [7, 2, 'cpu', 0.3, 0.5, False]
+    n = inspect.signature(y.nms)
+    assert list(n.parameters) == ['bboxes', 'scores', 'threshold'] and n.parameters['threshold'].default == 0.25
+    m = y.YOLOLossV1(32, 7, 2, 20)
+    assert (m.S, m.B, m.C, m.batch_size, m.lambda_coord, m.lambda_noobj) == (7, 2, 20, 32, 5., .5)
+    assert len(m.state_dict()) == 0
+    with pytest.raises(ValueError):
+        y.YOLOLossV1(32, 7, 2, 20, coord_mode="nope")
+
+
+def test_compat_modules_import_like_the_reference():
+    """`from v1Loss import YOLOLossV1` / `from utils.utils import decoder, nms` with yolo_v1_b200/compat on
+    sys.path (how INTEGRATION.md wires train.py / eval.py)."""
+    import importlib
+    import os
+    import sys
+    compat = os.path.join(os.path.dirname(y.__file__), "compat")
+    sys.path.insert(0, compat)
+    saved = {k: sys.modules.pop(k, None) for k in ("utils", "utils.utils", "v1Loss")}
+    try:
+        v1 = importlib.import_module("v1Loss")
+        uu = importlib.import_module("utils.utils")
+        assert v1.YOLOLossV1 is y.YOLOLossV1
+        assert uu.decoder is y.decoder and uu.nms is y.nms
+        assert uu.compute_iou_matrix is y.compute_iou_matrix
+        assert len(uu.VOC_CLASSES) == 20
+    finally:
+        sys.path.remove(compat)
+        for k in ("utils", "utils.utils", "v1Loss"):
+            sys.modules.pop(k, None)
+            if saved[k] is not None:
+                sys.modules[k] = saved[k]
+
+
+def test_helper_functions_cpu():
+    b1 = torch.tensor([[10., 20., 100., 123.], [200., 300., 300., 350.]])
+    b2 = torch.tensor([[50., 60., 150., 120.], [0., 10., 123., 150.], [170., 190., 310., 400.]])
+    iou = y.compute_iou_matrix(b1, b2)          # utils/utils.py:506-525 print-only fixture
+    assert np.allclose(iou.numpy(), [[0.24449877, 0.53832752, 0.0], [0.0, 0.0, 0.17006803]], atol=1e-7)
+    with pytest.raises(TypeError):
+        y.compute_iou_matrix([[0, 0, 1, 1]], b2)
+    out = y.convert_CxCyWH_to_X1Y1X2Y2(torch.tensor([[0.5, 0.5, 0.2, 0.4]]), 7)
+    assert np.allclose(out.numpy(), [[0.5 / 7 - 0.1, 0.5 / 7 - 0.2, 0.5 / 7 + 0.1, 0.5 / 7 + 0.2]])
+    with pytest.raises(AssertionError):
+        y.convert_CxCyWH_to_X1Y1X2Y2(torch.zeros(2, 3), 7)
+
+
+def test_synth_targets_follow_the_encoder_format():
+    pred, target = synth.make_loss_inputs(64, 7, seed=1)
+    obj = target[..., 0] == 1
+    assert 0 < int(obj.sum()) < 64 * 49
+    assert torch.equal(target[..., 0], target[..., 1])                    # both confidence slots
+    assert torch.equal(target[..., 2:6], target[..., 6:10])               # same box in both slots
+    assert torch.equal(target[..., 10:].sum(-1), obj.float())             # one-hot class on object cells only
+    assert float(target[~obj].abs().sum()) == 0
+    assert float(pred.min()) >= 0.01 and float(pred.max()) <= 0.99
+    p2, n = synth.make_tie_free_decode_inputs(128, 7, seed=2)
+    assert synth.score_tie_images(p2).numel() == 0 and n >= 0

@@ -1,0 +1,411 @@
+// decode_nms.cu -- K2 (decode) and K3 (bitmask NMS), and their per-image fusion (sm_100a).
+//
+// Replaces decoder (reference utils/utils.py:94-147) and nms (utils/utils.py:150-184).
+// Specification: SURVEY.md Appendix B.  Built with -fmad=false: every fp32 operation rounds on its own,
+// exactly like the reference's ATen CPU ops, so candidates, scores and keep lists are bit-exact.
+//
+// One CTA per image; an image's candidates never leave shared memory in the fused kernel:
+//   load   : the image's S*S*D values -> shared (coalesced)
+//   decode : max confidence (block reduce), per (cell, slot) candidate test, class arg-max, score,
+//            `double(score) > thresh`, order-preserving compaction (ballot + prefix) = emission order
+//   sort   : rank by counting (score descending, emission index ascending) -- deterministic, no ties left
+//   mask   : suppression bit-matrix; a warp takes a row i, lane <-> column j, __ballot_sync builds the word
+//            (dies iff !(IoU <= thr), utils/utils.py:180; the image tile is reused for the matrix)
+//   sweep  : one warp walks the sorted boxes word by word; lane w holds word w of the removed-set; a kept
+//            box ORs its row in.  A suppressed box never suppresses (iterated semantics of the reference).
+//   store  : kept detections in descending score order (float4 boxes), counts.
+#include "common.cuh"
+
+namespace yolo1 {
+namespace {
+
+constexpr int kMaxCand = 1024;
+
+struct DecodeParams {
+  const void* pred;
+  int64_t st[4];
+  int S, B, C;
+  float cs;       // fl32(1/S), utils/utils.py:105
+  double thresh;  // python double, utils/utils.py:129
+  float iou_thr;
+  int per_class;
+  // decode outputs / nms inputs
+  float* boxes;
+  float* scores;
+  int32_t* cls;
+  int32_t* counts;
+  // nms / fused outputs
+  float* out_boxes;
+  float* out_scores;
+  int32_t* out_cls;
+  int32_t* keep;
+  int32_t* out_counts;
+  int32_t* cand_counts;
+  int max_n;
+};
+
+// dynamic shared memory layout shared by the three kernels
+struct Smem {
+  float* img;       // [S*S*D]   (decode)   -- aliased by mask after decode
+  uint32_t* mask;   // [n * W]
+  float4* box;      // [max_n]  candidates in emission order
+  float* score;     // [max_n]
+  int32_t* cls;     // [max_n]
+  float4* sbox;     // [max_n]  sorted by score
+  float* sarea;     // [max_n]
+  int32_t* sidx;    // [max_n]  sorted position -> emission index
+  int32_t* keep;    // [max_n]  kept sorted positions
+  int32_t* misc;    // [64]
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+__host__ __device__ inline size_t smem_layout(unsigned char* base, int img_floats, int max_n, Smem* s) {
+  const int W = (max_n + 31) / 32;
+  size_t region = (size_t)img_floats * 4;
+  const size_t mask_bytes = (size_t)max_n * W * 4;
+  if (mask_bytes > region) region = mask_bytes;
+  size_t off = 0;
+  if (s) s->img = reinterpret_cast<float*>(base), s->mask = reinterpret_cast<uint32_t*>(base);
+  off += align16(region);
+  if (s) s->box = reinterpret_cast<float4*>(base + off);
+  off += (size_t)max_n * 16;
+  if (s) s->sbox = reinterpret_cast<float4*>(base + off);
+  off += (size_t)max_n * 16;
+  if (s) s->score = reinterpret_cast<float*>(base + off);
+  off += align16((size_t)max_n * 4);
+  if (s) s->cls = reinterpret_cast<int32_t*>(base + off);
+  off += align16((size_t)max_n * 4);
+  if (s) s->sarea = reinterpret_cast<float*>(base + off);
+  off += align16((size_t)max_n * 4);
+  if (s) s->sidx = reinterpret_cast<int32_t*>(base + off);
+  off += align16((size_t)max_n * 4);
+  if (s) s->keep = reinterpret_cast<int32_t*>(base + off);
+  off += align16((size_t)max_n * 4);
+  if (s) s->misc = reinterpret_cast<int32_t*>(base + off);
+  off += 64 * 4;
+  return off;
+}
+
+// ---- phase: load one image into shared memory as [cell][channel] floats ---------------------------------
+template <typename E>
+__device__ __forceinline__ void load_image(const DecodeParams& p, int64_t n, float* img) {
+  const int S = p.S, D = 5 * p.B + p.C, total = S * S * D;
+  const E* base = reinterpret_cast<const E*>(p.pred) + n * p.st[0];
+  const bool dense = p.st[3] == 1 && p.st[2] == D && p.st[1] == (int64_t)S * D;
+  if (dense) {
+    for (int t = threadIdx.x; t < total; t += blockDim.x) img[t] = ld_elem(base + t);
+  } else {
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+      const int cell = t / D, c = t - cell * D;
+      const int i = cell / S, j = cell - i * S;
+      img[t] = ld_elem(base + i * p.st[1] + j * p.st[2] + c * p.st[3]);
+    }
+  }
+}
+
+// ---- phase: decode (utils/utils.py:108-132).  Returns the candidate count (uniform over the CTA). -----
+__device__ __forceinline__ int decode_phase(const DecodeParams& p, const Smem& sm) {
+  const int S = p.S, B = p.B, C = p.C, D = 5 * B + C, slots = S * S * B;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  float* red = reinterpret_cast<float*>(sm.misc);  // [32] floats, then [32] ints
+  int* wcount = sm.misc + 32;
+  // :109-113 max over the confidences of the image
+  float mx = -INFINITY;
+  for (int t = threadIdx.x; t < slots; t += blockDim.x) {
+    const int cell = t / B, b = t - cell * B;
+    mx = fmaxf(mx, sm.img[cell * D + b]);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int w = 1; w < nwarps; ++w) mx = fmaxf(mx, red[w]);
+  __syncthreads();
+
+  int base = 0;  // candidates emitted by earlier rounds (uniform)
+  for (int t0 = 0; t0 < slots; t0 += blockDim.x) {
+    const int t = t0 + threadIdx.x;
+    bool pass = false;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float score = 0.f;
+    int best_c = 0;
+    if (t < slots) {
+      const int cell = t / B, b = t - cell * B;
+      const int i = cell / S, j = cell - i * S;
+      const float* P = sm.img + cell * D;
+      const float conf = P[b];
+      if (conf > 0.0001f || conf == mx) {  // :108-114
+        float best_p = P[5 * B];
+        for (int c = 1; c < C; ++c) {      // :127 first arg-max
+          const float v = P[5 * B + c];
+          if (v > best_p) best_p = v, best_c = c;
+        }
+        score = conf * best_p;             // :129
+        if ((double)score > p.thresh) {
+          pass = true;
+          const float x = P[B + 4 * b], y = P[B + 4 * b + 1], w = P[B + 4 * b + 2], h = P[B + 4 * b + 3];
+          const float cx = x * p.cs + (float)j * p.cs;  // :122-123 (no FMA: file is built with -fmad=false)
+          const float cy = y * p.cs + (float)i * p.cs;
+          const float hw = 0.5f * w, hh = 0.5f * h;
+          bx = make_float4(cx - hw, cy - hh, cx + hw, cy + hh);  // :124-126
+        }
+      }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) wcount[warp] = __popc(bal);
+    __syncthreads();
+    int before = base, total = 0;
+    for (int w = 0; w < nwarps; ++w) {
+      const int cw = wcount[w];
+      if (w < warp) before += cw;
+      total += cw;
+    }
+    if (pass) {
+      const int k = before + __popc(bal & ((1u << lane) - 1u));
+      sm.box[k] = bx;
+      sm.score[k] = score;
+      sm.cls[k] = best_c;
+    }
+    base += total;
+    __syncthreads();
+  }
+  return base;
+}
+
+// ---- phase: rank sort + suppression matrix + sweep (utils/utils.py:150-184).  Returns kept count. --------
+__device__ __forceinline__ int nms_phase(const Smem& sm, int n, float thr, int per_class) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int W = (n + 31) >> 5;
+  // :161 order = scores descending; ties -> lower emission index first (canonical)
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const float s = sm.score[k];
+    int rank = 0;
+    for (int m = 0; m < n; ++m) {
+      const float sm_ = sm.score[m];
+      rank += (sm_ > s) || (sm_ == s && m < k);
+    }
+    const float4 b = sm.box[k];
+    sm.sbox[rank] = b;
+    sm.sarea[rank] = (b.z - b.x) * (b.w - b.y);  // :159
+    sm.sidx[rank] = k;
+  }
+  __syncthreads();
+  // suppression matrix: row i, bit j (j > i) set iff box j dies when box i is kept (:166-180)
+  for (int item = warp; item < n * W; item += nwarps) {
+    const int i = item / W, w = item - i * W;
+    if (w < (i >> 5)) continue;  // columns before i are never consulted
+    const int j = (w << 5) + lane;
+    bool dead = false;
+    if (j > i && j < n) {
+      const float4 A = sm.sbox[i], Bx = sm.sbox[j];
+      const float xx1 = Bx.x < A.x ? A.x : Bx.x;  // clamp(min=x1[i])
+      const float yy1 = Bx.y < A.y ? A.y : Bx.y;
+      const float xx2 = Bx.z > A.z ? A.z : Bx.z;  // clamp(max=x2[i])
+      const float yy2 = Bx.w > A.w ? A.w : Bx.w;
+      float ww = xx2 - xx1, hh = yy2 - yy1;
+      if (ww < 0.f) ww = 0.f;
+      if (hh < 0.f) hh = 0.f;
+      const float inter = ww * hh;
+      const float ovr = inter / ((sm.sarea[i] + sm.sarea[j]) - inter);
+      dead = !(ovr <= thr);
+      if (per_class && sm.cls[sm.sidx[i]] != sm.cls[sm.sidx[j]]) dead = false;
+    }
+    const unsigned bits = __ballot_sync(0xffffffffu, dead);
+    if (lane == 0) sm.mask[item] = bits;
+  }
+  __syncthreads();
+  // sweep: warp 0; lane w owns word w of the removed set (n <= 1024 -> W <= 32)
+  if (warp == 0) {
+    unsigned removed = 0;
+    int kept = 0;
+    for (int w = 0; w < W; ++w) {
+      const unsigned valid = (w == W - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+      unsigned alive = ~__shfl_sync(0xffffffffu, removed, w) & valid;
+      while (alive) {
+        const int b = __ffs(alive) - 1;
+        const int i = (w << 5) + b;
+        if (lane == 0) sm.keep[kept] = i;
+        ++kept;
+        const unsigned row = (lane >= w && lane < W) ? sm.mask[i * W + lane] : 0u;
+        removed |= row;
+        alive &= ~__shfl_sync(0xffffffffu, row, w);
+        alive &= ~(1u << b);
+      }
+    }
+    if (lane == 0) sm.misc[0] = kept;
+  }
+  __syncthreads();
+  return sm.misc[0];
+}
+
+// ---- kernels ---------------------------------------------------------------------------------------------
+template <typename E>
+__global__ void decode_nms_kernel(const __grid_constant__ DecodeParams p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  Smem sm;
+  smem_layout(raw, p.S * p.S * (5 * p.B + p.C), p.max_n, &sm);
+  const int64_t n = blockIdx.x;
+  load_image<E>(p, n, sm.img);
+  __syncthreads();
+  const int cand = decode_phase(p, sm);
+  const int kept = cand > 0 ? nms_phase(sm, cand, p.iou_thr, p.per_class) : 0;
+  for (int t = threadIdx.x; t < kept; t += blockDim.x) {
+    const int src = sm.keep[t], e = sm.sidx[src];
+    const int64_t dst = n * p.max_n + t;
+    reinterpret_cast<float4*>(p.out_boxes)[dst] = sm.sbox[src];
+    p.out_scores[dst] = sm.score[e];
+    p.out_cls[dst] = sm.cls[e];
+    if (p.keep) p.keep[dst] = e;
+  }
+  for (int t = kept + threadIdx.x; t < p.max_n; t += blockDim.x) {  // rows beyond the count are zero
+    const int64_t dst = n * p.max_n + t;
+    reinterpret_cast<float4*>(p.out_boxes)[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+    p.out_scores[dst] = 0.f;
+    p.out_cls[dst] = 0;
+    if (p.keep) p.keep[dst] = 0;
+  }
+  if (threadIdx.x == 0) {
+    p.out_counts[n] = kept;
+    if (p.cand_counts) p.cand_counts[n] = cand;
+  }
+}
+
+template <typename E>
+__global__ void decode_kernel(const __grid_constant__ DecodeParams p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  Smem sm;
+  smem_layout(raw, p.S * p.S * (5 * p.B + p.C), p.max_n, &sm);
+  const int64_t n = blockIdx.x;
+  load_image<E>(p, n, sm.img);
+  __syncthreads();
+  const int cand = decode_phase(p, sm);
+  for (int t = threadIdx.x; t < cand; t += blockDim.x) {
+    const int64_t dst = n * p.max_n + t;
+    reinterpret_cast<float4*>(p.boxes)[dst] = sm.box[t];
+    p.scores[dst] = sm.score[t];
+    p.cls[dst] = sm.cls[t];
+  }
+  for (int t = cand + threadIdx.x; t < p.max_n; t += blockDim.x) {
+    const int64_t dst = n * p.max_n + t;
+    reinterpret_cast<float4*>(p.boxes)[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
+    p.scores[dst] = 0.f;
+    p.cls[dst] = 0;
+  }
+  if (threadIdx.x == 0) p.counts[n] = cand;
+}
+
+__global__ void nms_kernel(const __grid_constant__ DecodeParams p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  Smem sm;
+  smem_layout(raw, 0, p.max_n, &sm);
+  const int64_t n = blockIdx.x;
+  int cnt = p.counts[n];
+  cnt = cnt < 0 ? 0 : (cnt > p.max_n ? p.max_n : cnt);
+  for (int t = threadIdx.x; t < cnt; t += blockDim.x) {
+    const int64_t src = n * p.max_n + t;
+    const float* b = p.boxes + 4 * src;  // caller memory: only 4-byte alignment is required
+    sm.box[t] = make_float4(b[0], b[1], b[2], b[3]);
+    sm.score[t] = p.scores[src];
+    sm.cls[t] = p.cls ? p.cls[src] : 0;
+  }
+  __syncthreads();
+  const int kept = cnt > 0 ? nms_phase(sm, cnt, p.iou_thr, p.per_class) : 0;
+  for (int t = threadIdx.x; t < p.max_n; t += blockDim.x)
+    p.keep[n * p.max_n + t] = t < kept ? sm.sidx[sm.keep[t]] : 0;
+  if (threadIdx.x == 0) p.out_counts[n] = kept;
+}
+
+int block_threads(int max_n) { return max_n <= 128 ? 128 : 256; }
+
+template <typename K>
+int launch(K kern, const DecodeParams& p, int64_t N, int img_floats, cudaStream_t stream) {
+  if (N == 0) return 0;
+  const size_t smem = smem_layout(nullptr, img_floats, p.max_n, nullptr);
+  if (smem > 227 * 1024) return YOLO1_ERR_UNSUPPORTED;
+  YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)N, block_threads(p.max_n), smem, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+int check_decode_args(const void* pred, const int64_t st[4], int dtype, int64_t N, int S, int B, int C) {
+  if (!pred || !st || N < 0 || S <= 0 || B <= 0 || C <= 0) return YOLO1_ERR_ARG;
+  if (dtype != YOLO1_DTYPE_F32 && dtype != YOLO1_DTYPE_BF16) return YOLO1_ERR_ARG;
+  if (N > 0x7fffffffll) return YOLO1_ERR_UNSUPPORTED;  // one CTA per image
+  if ((int64_t)S * S * B > kMaxCand || 5 * B + C > 128) return YOLO1_ERR_UNSUPPORTED;
+  if ((uintptr_t)pred % (dtype == YOLO1_DTYPE_F32 ? 4 : 2)) return YOLO1_ERR_ALIGN;
+  return 0;
+}
+
+void fill_decode(DecodeParams& p, const void* pred, const int64_t st[4], int S, int B, int C, double thresh) {
+  p = DecodeParams{};
+  p.pred = pred;
+  for (int d = 0; d < 4; ++d) p.st[d] = st[d];
+  p.S = S, p.B = B, p.C = C;
+  p.cs = (float)(1.0 / (double)S);
+  p.thresh = thresh;
+  p.max_n = S * S * B;
+}
+
+}  // namespace
+}  // namespace yolo1
+
+extern "C" {
+
+int yolo1_decode(const void* pred, const int64_t pred_strides[4], int pred_dtype, int64_t N, int S, int B, int C,
+                 double thresh, float* boxes, float* scores, int32_t* cls, int32_t* counts, void* stream) {
+  using namespace yolo1;
+  int rc = check_decode_args(pred, pred_strides, pred_dtype, N, S, B, C);
+  if (rc) return rc;
+  if (!boxes || !scores || !cls || !counts) return YOLO1_ERR_ARG;
+  if ((uintptr_t)boxes % 16 || (uintptr_t)scores % 4 || (uintptr_t)cls % 4 || (uintptr_t)counts % 4)
+    return YOLO1_ERR_ALIGN;
+  DecodeParams p;
+  fill_decode(p, pred, pred_strides, S, B, C, thresh);
+  p.boxes = boxes, p.scores = scores, p.cls = cls, p.counts = counts;
+  const int img = S * S * (5 * B + C);
+  if (pred_dtype == YOLO1_DTYPE_BF16) return launch(decode_kernel<__nv_bfloat16>, p, N, img, (cudaStream_t)stream);
+  return launch(decode_kernel<float>, p, N, img, (cudaStream_t)stream);
+}
+
+int yolo1_nms(const float* boxes, const float* scores, const int32_t* cls, const int32_t* counts, int64_t N,
+              int max_n, float iou_thr, int per_class, int32_t* keep, int32_t* keep_counts, void* stream) {
+  using namespace yolo1;
+  if (!boxes || !scores || !counts || !keep || !keep_counts || N < 0 || max_n <= 0) return YOLO1_ERR_ARG;
+  if (per_class && !cls) return YOLO1_ERR_ARG;
+  if (max_n > kMaxCand || N > 0x7fffffffll) return YOLO1_ERR_UNSUPPORTED;
+  if ((uintptr_t)boxes % 4 || (uintptr_t)scores % 4 || (cls && (uintptr_t)cls % 4) || (uintptr_t)counts % 4 ||
+      (uintptr_t)keep % 4 || (uintptr_t)keep_counts % 4)
+    return YOLO1_ERR_ALIGN;
+  DecodeParams p = DecodeParams{};
+  p.boxes = const_cast<float*>(boxes), p.scores = const_cast<float*>(scores), p.cls = const_cast<int32_t*>(cls);
+  p.counts = const_cast<int32_t*>(counts);
+  p.keep = keep, p.out_counts = keep_counts;
+  p.max_n = max_n, p.iou_thr = iou_thr, p.per_class = per_class ? 1 : 0;
+  return launch(nms_kernel, p, N, 0, (cudaStream_t)stream);
+}
+
+int yolo1_decode_nms(const void* pred, const int64_t pred_strides[4], int pred_dtype, int64_t N, int S, int B,
+                     int C, double thresh, float iou_thr, int per_class, float* out_boxes, float* out_scores,
+                     int32_t* out_cls, int32_t* out_counts, int32_t* keep_idx, int32_t* cand_counts,
+                     void* stream) {
+  using namespace yolo1;
+  int rc = check_decode_args(pred, pred_strides, pred_dtype, N, S, B, C);
+  if (rc) return rc;
+  if (!out_boxes || !out_scores || !out_cls || !out_counts) return YOLO1_ERR_ARG;
+  if ((uintptr_t)out_boxes % 16 || (uintptr_t)out_scores % 4 || (uintptr_t)out_cls % 4 ||
+      (uintptr_t)out_counts % 4 || (keep_idx && (uintptr_t)keep_idx % 4) ||
+      (cand_counts && (uintptr_t)cand_counts % 4))
+    return YOLO1_ERR_ALIGN;
+  DecodeParams p;
+  fill_decode(p, pred, pred_strides, S, B, C, thresh);
+  p.iou_thr = iou_thr, p.per_class = per_class ? 1 : 0;
+  p.out_boxes = out_boxes, p.out_scores = out_scores, p.out_cls = out_cls, p.out_counts = out_counts;
+  p.keep = keep_idx, p.cand_counts = cand_counts;
+  const int img = S * S * (5 * B + C);
+  if (pred_dtype == YOLO1_DTYPE_BF16)
+    return launch(decode_nms_kernel<__nv_bfloat16>, p, N, img, (cudaStream_t)stream);
+  return launch(decode_nms_kernel<float>, p, N, img, (cudaStream_t)stream);
+}
+
+}  // extern "C"

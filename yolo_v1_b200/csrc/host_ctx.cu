@@ -1,0 +1,245 @@
+// host_ctx.cu -- host-buffer entry points: the same kernels for callers that hold HOST memory.
+//
+// The reference's call sites hand the loss / decoder CPU tensors when run with device='cpu'
+// (v1Loss.py:10 `_device`, utils/utils.py:94 `device='cpu'`).  A context owns three sets of device staging
+// buffers and three streams (H2D, compute, D2H); a batch is cut into chunks of `chunk_images` images and
+// chunk c+1's upload, chunk c's kernel and chunk c-1's download overlap (PCIe is full duplex, the copy
+// engines are independent of the SMs).  The calls block until the results are in the caller's buffers.
+// The loss call's "first two objects of the call" rule (v1Loss.py:101) spans chunks through the carry
+// counter in the loss workspace (loss.cu), so a chunked call equals one un-chunked call.
+#include <new>
+
+#include "common.cuh"
+
+namespace yolo1 {
+int loss_launch_chunk(const void* pred, const int64_t ps[4], int pred_dtype, const float* target,
+                      const int64_t ts[4], void* grad, const int64_t gs[4], float* terms, int64_t N, int S,
+                      int B, int C, float lambda_coord, float lambda_noobj, float inv_batch_size, int coord_mode,
+                      void* workspace, size_t workspace_bytes, int chunk_flags, int variant, cudaStream_t stream);
+}
+
+namespace {
+constexpr int kBuf = 3;
+}
+
+struct yolo1_host_ctx {
+  int device, S, B, C, D, max_n;
+  int64_t chunk;  // images per chunk
+  cudaStream_t s_in, s_k, s_out;
+  cudaEvent_t in_done[kBuf], k_done[kBuf], out_done[kBuf];
+  float *d_pred[kBuf], *d_tgt[kBuf], *d_grad[kBuf];
+  float *d_boxes[kBuf], *d_scores[kBuf];
+  int32_t *d_cls[kBuf], *d_counts[kBuf];
+  void* d_ws;
+  size_t ws_bytes;
+  float* d_terms;
+  float* h_terms;  // pinned
+};
+
+namespace {
+
+void free_ctx(yolo1_host_ctx* c) {
+  if (!c) return;
+  for (int b = 0; b < kBuf; ++b) {
+    cudaFree(c->d_pred[b]), cudaFree(c->d_tgt[b]), cudaFree(c->d_grad[b]);
+    cudaFree(c->d_boxes[b]), cudaFree(c->d_scores[b]), cudaFree(c->d_cls[b]), cudaFree(c->d_counts[b]);
+    if (c->in_done[b]) cudaEventDestroy(c->in_done[b]);
+    if (c->k_done[b]) cudaEventDestroy(c->k_done[b]);
+    if (c->out_done[b]) cudaEventDestroy(c->out_done[b]);
+  }
+  cudaFree(c->d_ws), cudaFree(c->d_terms);
+  if (c->h_terms) cudaFreeHost(c->h_terms);
+  if (c->s_in) cudaStreamDestroy(c->s_in);
+  if (c->s_k) cudaStreamDestroy(c->s_k);
+  if (c->s_out) cudaStreamDestroy(c->s_out);
+  delete c;
+}
+
+// decode outputs are allocated on first use (a loss-only caller never pays for them)
+int ensure_decode_buffers(yolo1_host_ctx* c) {
+  if (c->d_boxes[0]) return 0;
+  for (int b = 0; b < kBuf; ++b) {
+    YOLO1_CUDA_TRY(cudaMalloc(&c->d_boxes[b], (size_t)c->chunk * c->max_n * 16));
+    YOLO1_CUDA_TRY(cudaMalloc(&c->d_scores[b], (size_t)c->chunk * c->max_n * 4));
+    YOLO1_CUDA_TRY(cudaMalloc(&c->d_cls[b], (size_t)c->chunk * c->max_n * 4));
+    YOLO1_CUDA_TRY(cudaMalloc(&c->d_counts[b], (size_t)c->chunk * 4));
+  }
+  return 0;
+}
+int ensure_loss_buffers(yolo1_host_ctx* c) {
+  if (c->d_tgt[0]) return 0;
+  const size_t bytes = (size_t)c->chunk * c->S * c->S * c->D * 4;
+  for (int b = 0; b < kBuf; ++b) {
+    YOLO1_CUDA_TRY(cudaMalloc(&c->d_tgt[b], bytes));
+    YOLO1_CUDA_TRY(cudaMalloc(&c->d_grad[b], bytes));
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int yolo1_host_ctx_create(yolo1_host_ctx** out, int device, int S, int B, int C, int64_t chunk_images) {
+  if (!out || S <= 0 || B <= 0 || C <= 0 || chunk_images < 0) return YOLO1_ERR_ARG;
+  if (B > 8 || 5 * B + C > 128 || (int64_t)S * S * B > 1024) return YOLO1_ERR_UNSUPPORTED;
+  *out = nullptr;
+  YOLO1_CUDA_TRY(cudaSetDevice(device));
+  yolo1_host_ctx* c = new (std::nothrow) yolo1_host_ctx();
+  if (!c) return (int)cudaErrorMemoryAllocation;
+  c->device = device, c->S = S, c->B = B, c->C = C, c->D = 5 * B + C, c->max_n = S * S * B;
+  const size_t img_bytes = (size_t)S * S * c->D * 4;
+  // default: ~24 MB per tensor per chunk -- long enough for PCIe to reach its plateau, short enough that the
+  // pipeline fill/drain (one chunk each) is a small part of a large batch
+  c->chunk = chunk_images > 0 ? chunk_images : (int64_t)((24u << 20) / img_bytes > 0 ? (24u << 20) / img_bytes : 1);
+  int rc = 0;
+  auto fail = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == 0) rc = (int)e;
+  };
+  fail(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+  fail(cudaStreamCreateWithFlags(&c->s_k, cudaStreamNonBlocking));
+  fail(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+  for (int b = 0; b < kBuf && rc == 0; ++b) {
+    fail(cudaEventCreateWithFlags(&c->in_done[b], cudaEventDisableTiming));
+    fail(cudaEventCreateWithFlags(&c->k_done[b], cudaEventDisableTiming));
+    fail(cudaEventCreateWithFlags(&c->out_done[b], cudaEventDisableTiming));
+    fail(cudaMalloc(&c->d_pred[b], (size_t)c->chunk * img_bytes));
+  }
+  c->ws_bytes = yolo1_loss_workspace_bytes(0, S, B, C);
+  fail(cudaMalloc(&c->d_ws, c->ws_bytes));
+  fail(cudaMalloc(&c->d_terms, 5 * sizeof(float)));
+  fail(cudaMallocHost(&c->h_terms, 5 * sizeof(float)));
+  if (rc) {
+    free_ctx(c);
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+void yolo1_host_ctx_destroy(yolo1_host_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  free_ctx(c);
+}
+
+int yolo1_host_pin(void* ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return YOLO1_ERR_ARG;
+  return (int)cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
+}
+int yolo1_host_unpin(void* ptr) {
+  if (!ptr) return YOLO1_ERR_ARG;
+  return (int)cudaHostUnregister(ptr);
+}
+
+int yolo1_loss_fwd_bwd_host(yolo1_host_ctx* c, const float* pred, const float* target, float* grad,
+                            float terms[5], int64_t N, float lambda_coord, float lambda_noobj,
+                            float inv_batch_size, int coord_mode) {
+  if (!c || !pred || !target || !terms || N < 0) return YOLO1_ERR_ARG;
+  if (coord_mode != YOLO1_COORD_REFERENCE && coord_mode != YOLO1_COORD_PAPER) return YOLO1_ERR_ARG;
+  YOLO1_CUDA_TRY(cudaSetDevice(c->device));
+  int rc = ensure_loss_buffers(c);
+  if (rc) return rc;
+  const int S = c->S, D = c->D;
+  const int64_t img = (int64_t)S * S * D;
+  const int64_t st[4] = {img, (int64_t)S * D, D, 1};
+  const int64_t nchunks = N == 0 ? 1 : (N + c->chunk - 1) / c->chunk;
+  for (int64_t k = 0; k < nchunks; ++k) {
+    const int b = (int)(k % kBuf);
+    const int64_t n0 = k * c->chunk, n = (N - n0 < c->chunk) ? N - n0 : c->chunk;
+    const size_t bytes = (size_t)n * img * 4;
+    // upload: the kernel that last read these staging buffers must be done
+    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
+    if (bytes) {
+      YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_pred[b], pred + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
+      YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_tgt[b], target + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
+    }
+    YOLO1_CUDA_TRY(cudaEventRecord(c->in_done[b], c->s_in));
+    // compute: inputs uploaded, previous download of this gradient buffer done
+    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
+    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->out_done[b], 0));
+    const int flags = (k == 0 ? 1 : 0) | (k == nchunks - 1 ? 2 : 0);
+    rc = yolo1::loss_launch_chunk(c->d_pred[b], st, YOLO1_DTYPE_F32, c->d_tgt[b], st, grad ? c->d_grad[b] : nullptr,
+                                  st, c->d_terms, n, S, c->B, c->C, lambda_coord, lambda_noobj, inv_batch_size,
+                                  coord_mode, c->d_ws, c->ws_bytes, flags, 0, c->s_k);
+    if (rc) break;
+    YOLO1_CUDA_TRY(cudaEventRecord(c->k_done[b], c->s_k));
+    // download
+    if (grad) {
+      YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->k_done[b], 0));
+      if (bytes)
+        YOLO1_CUDA_TRY(cudaMemcpyAsync(grad + n0 * img, c->d_grad[b], bytes, cudaMemcpyDeviceToHost, c->s_out));
+      YOLO1_CUDA_TRY(cudaEventRecord(c->out_done[b], c->s_out));
+    }
+  }
+  if (rc == 0) {
+    cudaError_t e = cudaMemcpyAsync(c->h_terms, c->d_terms, 5 * sizeof(float), cudaMemcpyDeviceToHost, c->s_k);
+    if (e != cudaSuccess) rc = (int)e;
+  }
+  cudaError_t e1 = cudaStreamSynchronize(c->s_k), e2 = cudaStreamSynchronize(c->s_out),
+              e3 = cudaStreamSynchronize(c->s_in);
+  if (rc) return rc;
+  if (e1 != cudaSuccess) return (int)e1;
+  if (e2 != cudaSuccess) return (int)e2;
+  if (e3 != cudaSuccess) return (int)e3;
+  for (int t = 0; t < 5; ++t) terms[t] = c->h_terms[t];
+  return 0;
+}
+
+int yolo1_decode_nms_host(yolo1_host_ctx* c, const float* pred, int64_t N, double thresh, float iou_thr,
+                          int per_class, float* out_boxes, float* out_scores, int32_t* out_cls,
+                          int32_t* out_counts) {
+  if (!c || !pred || !out_boxes || !out_scores || !out_cls || !out_counts || N < 0) return YOLO1_ERR_ARG;
+  YOLO1_CUDA_TRY(cudaSetDevice(c->device));
+  int rc = ensure_decode_buffers(c);
+  if (rc) return rc;
+  const int S = c->S, D = c->D, M = c->max_n;
+  const int64_t img = (int64_t)S * S * D;
+  const int64_t st[4] = {img, (int64_t)S * D, D, 1};
+  const int64_t nchunks = (N + c->chunk - 1) / c->chunk;
+  for (int64_t k = 0; k < nchunks; ++k) {
+    const int b = (int)(k % kBuf);
+    const int64_t n0 = k * c->chunk, n = (N - n0 < c->chunk) ? N - n0 : c->chunk;
+    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
+    YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_pred[b], pred + n0 * img, (size_t)n * img * 4, cudaMemcpyHostToDevice,
+                                   c->s_in));
+    YOLO1_CUDA_TRY(cudaEventRecord(c->in_done[b], c->s_in));
+    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
+    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->out_done[b], 0));
+    rc = yolo1_decode_nms(c->d_pred[b], st, YOLO1_DTYPE_F32, n, S, c->B, c->C, thresh, iou_thr, per_class,
+                          c->d_boxes[b], c->d_scores[b], c->d_cls[b], c->d_counts[b], nullptr, nullptr, c->s_k);
+    if (rc) break;
+    YOLO1_CUDA_TRY(cudaEventRecord(c->k_done[b], c->s_k));
+    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->k_done[b], 0));
+    YOLO1_CUDA_TRY(cudaMemcpyAsync(out_boxes + n0 * M * 4, c->d_boxes[b], (size_t)n * M * 16,
+                                   cudaMemcpyDeviceToHost, c->s_out));
+    YOLO1_CUDA_TRY(cudaMemcpyAsync(out_scores + n0 * M, c->d_scores[b], (size_t)n * M * 4, cudaMemcpyDeviceToHost,
+                                   c->s_out));
+    YOLO1_CUDA_TRY(cudaMemcpyAsync(out_cls + n0 * M, c->d_cls[b], (size_t)n * M * 4, cudaMemcpyDeviceToHost,
+                                   c->s_out));
+    YOLO1_CUDA_TRY(cudaMemcpyAsync(out_counts + n0, c->d_counts[b], (size_t)n * 4, cudaMemcpyDeviceToHost,
+                                   c->s_out));
+    YOLO1_CUDA_TRY(cudaEventRecord(c->out_done[b], c->s_out));
+  }
+  cudaError_t e1 = cudaStreamSynchronize(c->s_k), e2 = cudaStreamSynchronize(c->s_out),
+              e3 = cudaStreamSynchronize(c->s_in);
+  if (rc) return rc;
+  if (e1 != cudaSuccess) return (int)e1;
+  if (e2 != cudaSuccess) return (int)e2;
+  if (e3 != cudaSuccess) return (int)e3;
+  return 0;
+}
+
+int yolo1_abi_version(void) { return YOLO1_ABI_VERSION; }
+
+const char* yolo1_error_string(int rc) {
+  if (rc == 0) return "success";
+  if (rc == YOLO1_ERR_ARG) return "yolo1: invalid argument (null pointer, negative size or bad enum)";
+  if (rc == YOLO1_ERR_UNSUPPORTED) return "yolo1: shape outside what the kernels are built for";
+  if (rc == YOLO1_ERR_ALIGN) return "yolo1: pointer not aligned to its element size";
+  if (rc < 0) return "yolo1: unknown library error";
+  return cudaGetErrorString((cudaError_t)rc);
+}
+
+}  // extern "C"
