@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path's headline benchmark (BASELINE.json metric: YOLOv1 loss fwd+bwd cells/s and
+decode+NMS images/s at 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on rank 0.  A "step" is one pass of the fused loss forward+backward over one batch of
+synthetic input (BASELINE config 3: N=65536, S=14, B=2, C=20 -> 12.8 M cells, 1.54 GB per tensor, larger than
+L2) PER GPU (weak scaling: every rank owns its own shard; the only collective is the all-reduce of the 5-float
+loss-terms vector, enqueued on a side stream).  `value` = cells all ranks processed / max-over-ranks device
+time with inputs resident in HBM; `e2e` = the same metric through the C ABI's host-buffer entry point
+(yolo1_loss_fwd_bwd_host: pinned host pred/target in, host gradient and terms out, copies inside the timed
+region).  `decode_nms` holds the second half of the metric (BASELINE config 2: 4096 images, S=7, thresh 0.1,
+IoU 0.5), measured the same way.  `roofline` and `cpu_baseline` as DESIGN.md describes.
+
+`--impl reference` times the reference's CPU algorithm for the same path: the reference is pure Python and
+cannot travel to the GPU box (/root/reference does not exist there), so this arm runs the C restatement in
+oracle/ (pinned to the reference by tests/golden) with all host threads -- cpu_baseline.kind = "port".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+S_LOSS, N_LOSS = 14, 65536          # BASELINE config 3 (per GPU)
+S_DEC, N_DEC = 7, 4096              # BASELINE config 2
+B, C, D = 2, 20, 30
+DEC_THRESH, DEC_IOU = 0.1, 0.5      # eval.py:94
+BYTES_PER_CELL = 360                # 120 B pred + 120 B target + 120 B grad (fp32)
+NMS_OPS_PER_PAIR = 13
+METRIC, UNIT = "yolov1_loss_fwd_bwd_cells_per_s", "cells/s"
+WORKLOAD = "config3: fused loss fwd+bwd, N=65536 per GPU, S=14, B=2, C=20, fp32, contiguous NHWC, ~3 objects/image"
+SEED = 20241018
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), float(j.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def _traffic(key):
+    """Per-launch DRAM bytes of the dominant kernel from the committed `ncu --set full` capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(p):
+        return json.load(open(p)).get(key)
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed regions (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    NAMES = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+
+    def __init__(self, gpu_id):
+        self.rows, self.proc, self.gpu_id = [], None, gpu_id
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_id), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, windows):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.06)
+        self.proc.terminate()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ts, line in self.rows:
+            if not any(a <= ts <= b + 0.05 for a, b in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1])), pw.append(float(f[2]))
+            except Exception:
+                continue
+            for name, v in zip(self.NAMES, f[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def _oracle_threads():
+    from oracle import oracle as O
+    return O.num_threads()
+
+
+def cpu_loss_baseline(pred_np, target_np, budget_s=10.0, max_images=None):
+    """The oracle port (OpenMP, all host threads) on a bounded sample of the same workload."""
+    from oracle import oracle as O
+    n = pred_np.shape[0] if max_images is None else min(max_images, pred_np.shape[0])
+    p, t = pred_np[:n], target_np[:n]
+    S = p.shape[1]
+    O.loss(p[:64], t[:64], batch_size=n)      # build/load + warm
+    t0 = time.perf_counter()
+    passes = 0
+    while True:
+        O.loss(p, t, batch_size=n)
+        passes += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or passes >= 50:
+            break
+    return {"value": n * S * S * passes / el, "unit": UNIT, "cores": _oracle_threads(), "kind": "port",
+            "sample": "%d passes over %d images (%d cells each) of the step's batch, loss+grad, %.1f s" %
+                      (passes, n, n * S * S, el)}
+
+
+def cpu_decode_baseline(pred_np, budget_s=8.0):
+    from oracle import oracle as O
+    n = pred_np.shape[0]
+    O.decode_nms(pred_np[:8], thresh=DEC_THRESH, nms_th=DEC_IOU)
+    t0 = time.perf_counter()
+    passes = 0
+    while True:
+        O.decode_nms(pred_np, thresh=DEC_THRESH, nms_th=DEC_IOU)
+        passes += 1
+        el = time.perf_counter() - t0
+        if el >= budget_s or passes >= 50:
+            break
+    return {"value": n * passes / el, "unit": "images/s", "cores": _oracle_threads(), "kind": "port",
+            "sample": "%d passes over the %d-image batch, %.1f s" % (passes, n, el)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """CPU arm: the reference algorithm (C port in oracle/) on the box's host cores, same metric/config."""
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from yolo_v1_b200 import synth
+    from oracle import oracle as O
+    n = 8192                       # bounded sample of config 3 per step (1.6 M cells)
+    pred, target = synth.make_loss_inputs(n, S_LOSS, seed=SEED + 3000)
+    p, t = pred.numpy(), target.numpy()
+    for _ in range(max(args.warmup, 1)):
+        O.loss(p, t, batch_size=n)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.loss(p, t, batch_size=n)
+    el = time.perf_counter() - t0
+    cells = n * S_LOSS * S_LOSS
+    value = cells * args.steps / el
+    dp, _ = synth.make_tie_free_decode_inputs(N_DEC, S_DEC, seed=2)
+    dnp = dp.numpy()
+    O.decode_nms(dnp, thresh=DEC_THRESH, nms_th=DEC_IOU)
+    t1 = time.perf_counter()
+    dsteps = max(1, min(args.steps, 20))
+    for _ in range(dsteps):
+        O.decode_nms(dnp, thresh=DEC_THRESH, nms_th=DEC_IOU)
+    dval = N_DEC * dsteps / (time.perf_counter() - t1)
+    cores = O.num_threads()
+    sample = "each step = loss+grad over %d images (%d cells) of config 3, OpenMP x%d" % (n, cells, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reference_step_sample_images": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "decode_nms": {"metric": "yolov1_decode_nms_images_per_s", "value": dval, "unit": "images/s",
+                       "e2e": {"value": dval, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                       "cpu_baseline": {"value": dval, "unit": "images/s", "cores": cores, "kind": "port",
+                                        "sample": "config 2 batch (4096 images), %d passes" % dsteps}},
+        "note": "the reference itself is pure Python/PyTorch and does not exist on the GPU box; this arm is the C "
+                "restatement in oracle/ (pinned to the reference's outputs by tests/golden). The unmodified "
+                "reference measured 8.9e3 cells/s (N=32,S=7) and 35.8 images/s in the build container "
+                "(SURVEY.md section 6).",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import yolo_v1_b200 as y
+    from yolo_v1_b200 import synth
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    hbm_peak, sm_max_mhz, peak_src = _peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    try:
+        gpu_id = str(torch.cuda.get_device_properties(dev).uuid)
+        gpu_id = gpu_id if gpu_id.startswith("GPU-") else "GPU-" + gpu_id
+    except Exception:
+        gpu_id = str(local_rank)
+    sampler = ClockSampler(gpu_id)
+    windows = []
+
+    # ---------------- loss: device-resident -------------------------------------------------------------
+    pred, target = synth.make_loss_inputs(N_LOSS, S_LOSS, seed=SEED + 3000 + rank, device=dev)
+    grad = torch.empty_like(pred)
+    terms = torch.empty(5, device=dev)
+    gterms = torch.empty(5, device=dev)
+    ws = torch.empty(1 << 17, dtype=torch.uint8, device=dev)
+    comm = torch.cuda.Stream(device=dev)
+    cells = N_LOSS * S_LOSS * S_LOSS
+
+    def loss_step():
+        y.yolo_loss_fused(pred, target, batch_size=N_LOSS, out_grad=grad, out_terms=terms, workspace=ws)
+        if world > 1:      # the path's only exchange: 20 bytes of loss terms, off the critical path
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(comm):
+                comm.wait_event(ev)
+                gterms.copy_(terms)
+                dist.all_reduce(gterms)
+
+    for _ in range(args.warmup):
+        loss_step()
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = sampler.mark()
+    e0.record()
+    for _ in range(args.steps):
+        loss_step()
+    e1.record()
+    comm.synchronize()
+    barrier()
+    windows.append((w0, sampler.mark()))
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = cells * world / (ms_step * 1e-3)
+    loss_value = float(terms[4].item())
+
+    # kernel-only duration for the roofline (same stream, events around the same launches, no collective)
+    for _ in range(3):
+        y.yolo_loss_fused(pred, target, batch_size=N_LOSS, out_grad=grad, out_terms=terms, workspace=ws)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(args.steps):
+        y.yolo_loss_fused(pred, target, batch_size=N_LOSS, out_grad=grad, out_terms=terms, workspace=ws)
+    k1.record()
+    torch.cuda.synchronize()
+    kern_ms = k0.elapsed_time(k1) / args.steps
+    achieved = BYTES_PER_CELL * cells / (kern_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                "traffic": _traffic("loss_tma_kernel_bytes_per_launch"), "kernel": "loss_tma_kernel<float,true,128,2,2>",
+                "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * cells, "peak_source": peak_src,
+                "frac_of_nominal_8TBs": achieved / 8000.0}
+
+    # ---------------- loss: end to end through the host-buffer C ABI ----------------------------------
+    e2e = None
+    hp = ht = None
+    if not args.no_e2e:
+        hp = torch.empty(pred.shape, dtype=torch.float32, pin_memory=True)
+        ht = torch.empty(pred.shape, dtype=torch.float32, pin_memory=True)
+        hg = torch.empty(pred.shape, dtype=torch.float32, pin_memory=True)
+        hp.copy_(pred), ht.copy_(target)
+        torch.cuda.synchronize()
+        ctx = y.HostContext(S_LOSS, B, C, device=local_rank)
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            hterms, _ = ctx.loss(hp, ht, batch_size=N_LOSS, out_grad=hg)
+        barrier()
+        w0 = sampler.mark()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            hterms, _ = ctx.loss(hp, ht, batch_size=N_LOSS, out_grad=hg)     # blocks until results are on the host
+        el = time.perf_counter() - t0
+        barrier()
+        windows.append((w0, sampler.mark()))
+        el_ms = max_over_ranks(el * 1e3)
+        assert abs(float(hterms[4]) - loss_value) <= 1e-5 * abs(loss_value)
+        assert torch.equal(hg[:256], grad[:256].cpu())
+        nbytes = pred.numel() * 4
+        e2e = {"value": cells * world * e2e_steps / (el_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 2 * nbytes,
+               "d2h_bytes_per_step": nbytes + 20, "steps": e2e_steps, "ms_per_step": el_ms / e2e_steps,
+               "api": "yolo1_loss_fwd_bwd_host (pinned host pred+target in, host grad+terms out)",
+               "pcie_gbs": 3 * nbytes * e2e_steps / (el_ms * 1e-3) / 1e9}
+        ctx.close()
+        del hg
+
+    # ---------------- decode + NMS (config 2) ----------------------------------------------------------
+    dpred_h, redrawn = synth.make_tie_free_decode_inputs(N_DEC, S_DEC, seed=2)
+    dpred = dpred_h.to(dev)
+    M = S_DEC * S_DEC * B
+    outs = (torch.empty((N_DEC, M, 4), device=dev), torch.empty((N_DEC, M), dtype=torch.int32, device=dev),
+            torch.empty((N_DEC, M), device=dev), torch.empty((N_DEC,), dtype=torch.int32, device=dev))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    dsteps = max(3, min(args.steps, 50))
+    for _ in range(args.warmup):
+        y.decode_nms_batched(dpred, DEC_THRESH, DEC_IOU, out=outs)
+    barrier()
+    dms = 0.0
+    w0 = sampler.mark()
+    for _ in range(dsteps):
+        flush.zero_()                                                  # L2 flush between timed iterations
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        y.decode_nms_batched(dpred, DEC_THRESH, DEC_IOU, out=outs)
+        b_.record()
+        b_.synchronize()
+        dms += a.elapsed_time(b_)
+    barrier()
+    windows.append((w0, sampler.mark()))
+    dms = max_over_ranks(dms) / dsteps
+    _, _, _, cnts, _, cand = y.decode_nms_batched(dpred, DEC_THRESH, DEC_IOU, return_keep=True)
+    cand = cand.cpu().numpy().astype(np.int64)
+    pairs = int((cand * (cand - 1) // 2).sum())
+    clocks = None
+    dec = {"metric": "yolov1_decode_nms_images_per_s", "value": N_DEC * world / (dms * 1e-3), "unit": "images/s",
+           "ms_per_step": dms, "steps": dsteps,
+           "config": {"workload": "config2: decode + class-agnostic NMS (the reference's decoder), 4096 images per "
+                                  "GPU, S=7, B=2, C=20, thresh 0.1, IoU 0.5, pred~U(0,1); L2 flushed between "
+                                  "timed iterations", "tie_redrawn_images": redrawn,
+                      "mean_candidates": float(cand.mean()), "mean_kept": float(cnts.float().mean().item())}}
+    if not args.no_e2e:
+        dh = dpred_h.pin_memory()
+        dctx = y.HostContext(S_DEC, B, C, device=local_rank)
+        out_h = dict(boxes=torch.empty((N_DEC, M, 4), pin_memory=True), scores=torch.empty((N_DEC, M), pin_memory=True),
+                     cls=torch.empty((N_DEC, M), dtype=torch.int32, pin_memory=True),
+                     counts=torch.empty((N_DEC,), dtype=torch.int32, pin_memory=True))
+        for _ in range(3):
+            dctx.decode_nms(dh, DEC_THRESH, DEC_IOU, out=out_h)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(dsteps):
+            dctx.decode_nms(dh, DEC_THRESH, DEC_IOU, out=out_h)
+        el_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+        assert torch.equal(out_h["counts"], cnts.cpu())
+        dec["e2e"] = {"value": N_DEC * world * dsteps / (el_ms * 1e-3), "unit": "images/s",
+                      "h2d_bytes_per_step": dh.numel() * 4, "d2h_bytes_per_step": N_DEC * (M * 24 + 4),
+                      "api": "yolo1_decode_nms_host"}
+        dctx.close()
+    clocks = sampler.stop(windows)
+    sm_mhz = clocks["sm_mhz"] or sm_max_mhz
+    fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12        # non-FMA fp32 lane-ops/s at the clock seen, Tops/s
+    ach = NMS_OPS_PER_PAIR * pairs / (dms * 1e-3) / 1e12
+    dec["roofline"] = {"bound": "fp32-pipe (not a contraction: no tensor cores)", "achieved": ach, "peak": fp32_peak,
+                       "unit": "Tops/s", "frac": ach / fp32_peak, "traffic": _traffic("decode_nms_kernel_bytes_per_launch"),
+                       "note": "13 fp32 ops per IoU pair x sum n(n-1)/2; small by construction -- the kernel is bound "
+                               "by shared-memory latency in the rank sort and the serial sweep, see DESIGN.md",
+                       "hbm_gbs": (N_DEC * S_DEC * S_DEC * D * 4 + int(cnts.sum().item()) * 24) / (dms * 1e-3) / 1e9}
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        pn = hp.numpy() if hp is not None else pred.cpu().numpy()
+        tn = ht.numpy() if ht is not None else target.cpu().numpy()
+        cpu = cpu_loss_baseline(pn, tn, budget_s=10.0, max_images=16384)
+        dec["cpu_baseline"] = cpu_decode_baseline(dpred_h.numpy(), budget_s=6.0)
+        # parity gate run with the benchmark: the oracle on a sub-batch of the very tensors that were timed
+        from oracle import oracle as O
+        o_terms, o_grad = O.loss(pn[:512], tn[:512], batch_size=N_LOSS)
+        _, g_small, t_small = y.yolo_loss_fused(pred[:512], target[:512], batch_size=N_LOSS)
+        err = float(np.abs(g_small.cpu().numpy() - o_grad).max() / np.abs(o_grad).max())
+        lerr = abs(float(t_small[4]) - float(o_terms[4])) / abs(float(o_terms[4]))
+        orc = O.decode_nms(dpred_h.numpy(), thresh=DEC_THRESH, nms_th=DEC_IOU)
+        bit_exact = bool(np.array_equal(orc["counts"], cnts.cpu().numpy()) and
+                         np.array_equal(orc["boxes"].view(np.uint32), outs[0].cpu().numpy().view(np.uint32)))
+        parity = {"loss_rel_err": lerr, "grad_rel_err": err, "tolerance": 1e-5, "decode_nms_bit_exact": bit_exact}
+        assert lerr <= 1e-5 and err <= 1e-5 and bit_exact, parity
+    else:
+        parity = None
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "cells_per_gpu": cells, "l2": "inputs (1.54 GB per tensor) larger than L2",
+                   "parallelism": "batch-sharded x%d, one 20-byte NCCL all-reduce of the loss terms per step on a side stream" % world
+                   if world > 1 else "single GPU", "timing": "CUDA events on the launch stream, max over ranks"},
+        "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "decode_nms": dec, "parity": parity, "loss": loss_value,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -135,7 +135,7 @@ def test_sentinel_empty_and_edge_cases():
     pred[0, 3, 4, 17] = 1.0
     ob, oc, os_ = O.decoder(pred.numpy(), thresh=1e-5)
     b, c, s = y.decoder(pred, thresh=1e-5)
-    assert len(os_) == 1 and np.array_equal(_bits(b.numpy()), _bits(ob)) and int(c[0]) == 17
+    assert len(os_) == 1 and np.array_equal(_bits(b.numpy()), _bits(ob)) and int(c[0]) == 7 == int(oc[0])
     assert np.array_equal(_bits(s.numpy()), _bits(os_))
     # all-zero image: every slot equals the max (0) but 0 > thresh fails -> sentinel
     b, c, s = y.decoder(torch.zeros(1, 7, 7, 30), thresh=0.0)

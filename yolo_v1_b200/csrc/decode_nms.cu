@@ -329,7 +329,8 @@ int launch(K kern, const DecodeParams& p, int64_t N, int img_floats, cudaStream_
 }
 
 int check_decode_args(const void* pred, const int64_t st[4], int dtype, int64_t N, int S, int B, int C) {
-  if (!pred || !st || N < 0 || S <= 0 || B <= 0 || C <= 0) return YOLO1_ERR_ARG;
+  if (!st || N < 0 || S <= 0 || B <= 0 || C <= 0) return YOLO1_ERR_ARG;
+  if (N > 0 && !pred) return YOLO1_ERR_ARG;
   if (dtype != YOLO1_DTYPE_F32 && dtype != YOLO1_DTYPE_BF16) return YOLO1_ERR_ARG;
   if (N > 0x7fffffffll) return YOLO1_ERR_UNSUPPORTED;  // one CTA per image
   if ((int64_t)S * S * B > kMaxCand || 5 * B + C > 128) return YOLO1_ERR_UNSUPPORTED;
@@ -357,6 +358,7 @@ int yolo1_decode(const void* pred, const int64_t pred_strides[4], int pred_dtype
   using namespace yolo1;
   int rc = check_decode_args(pred, pred_strides, pred_dtype, N, S, B, C);
   if (rc) return rc;
+  if (N == 0) return 0;
   if (!boxes || !scores || !cls || !counts) return YOLO1_ERR_ARG;
   if ((uintptr_t)boxes % 16 || (uintptr_t)scores % 4 || (uintptr_t)cls % 4 || (uintptr_t)counts % 4)
     return YOLO1_ERR_ALIGN;
@@ -371,7 +373,9 @@ int yolo1_decode(const void* pred, const int64_t pred_strides[4], int pred_dtype
 int yolo1_nms(const float* boxes, const float* scores, const int32_t* cls, const int32_t* counts, int64_t N,
               int max_n, float iou_thr, int per_class, int32_t* keep, int32_t* keep_counts, void* stream) {
   using namespace yolo1;
-  if (!boxes || !scores || !counts || !keep || !keep_counts || N < 0 || max_n <= 0) return YOLO1_ERR_ARG;
+  if (N < 0 || max_n <= 0) return YOLO1_ERR_ARG;
+  if (N == 0) return 0;
+  if (!boxes || !scores || !counts || !keep || !keep_counts) return YOLO1_ERR_ARG;
   if (per_class && !cls) return YOLO1_ERR_ARG;
   if (max_n > kMaxCand || N > 0x7fffffffll) return YOLO1_ERR_UNSUPPORTED;
   if ((uintptr_t)boxes % 4 || (uintptr_t)scores % 4 || (cls && (uintptr_t)cls % 4) || (uintptr_t)counts % 4 ||
@@ -392,6 +396,7 @@ int yolo1_decode_nms(const void* pred, const int64_t pred_strides[4], int pred_d
   using namespace yolo1;
   int rc = check_decode_args(pred, pred_strides, pred_dtype, N, S, B, C);
   if (rc) return rc;
+  if (N == 0) return 0;
   if (!out_boxes || !out_scores || !out_cls || !out_counts) return YOLO1_ERR_ARG;
   if ((uintptr_t)out_boxes % 16 || (uintptr_t)out_scores % 4 || (uintptr_t)out_cls % 4 ||
       (uintptr_t)out_counts % 4 || (keep_idx && (uintptr_t)keep_idx % 4) ||

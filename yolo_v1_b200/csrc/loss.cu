@@ -628,9 +628,10 @@ int loss_launch_chunk(const void* pred, const int64_t ps[4], int pred_dtype, con
                       const int64_t ts[4], void* grad, const int64_t gs[4], float* terms, int64_t N, int S,
                       int B, int C, float lambda_coord, float lambda_noobj, float inv_batch_size, int coord_mode,
                       void* workspace, size_t workspace_bytes, int chunk_flags, int variant, cudaStream_t stream) {
-  if (!pred || !target || !terms || !workspace || !ps || !ts) return YOLO1_ERR_ARG;
+  if (!terms || !workspace || !ps || !ts || N < 0) return YOLO1_ERR_ARG;
+  if (N > 0 && (!pred || !target)) return YOLO1_ERR_ARG;  // an empty batch may come with null data pointers
   if (grad && !gs) return YOLO1_ERR_ARG;
-  if (N < 0 || S <= 0 || B <= 0 || C < 0) return YOLO1_ERR_ARG;
+  if ( S <= 0 || B <= 0 || C < 0) return YOLO1_ERR_ARG;
   if (pred_dtype != YOLO1_DTYPE_F32 && pred_dtype != YOLO1_DTYPE_BF16) return YOLO1_ERR_ARG;
   if (coord_mode != YOLO1_COORD_REFERENCE && coord_mode != YOLO1_COORD_PAPER) return YOLO1_ERR_ARG;
   if (B > kMaxB || 5 * B + C > 128) return YOLO1_ERR_UNSUPPORTED;
