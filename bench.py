@@ -30,6 +30,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm / cpu_baseline must be allowed every host core
+# (libgomp reads this when it is first loaded, so it has to happen before numpy / torch are imported).
+if "TORCHELASTIC_RUN_ID" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
 
 S_LOSS, N_LOSS = 14, 65536          # BASELINE config 3 (per GPU)
 S_DEC, N_DEC = 7, 4096              # BASELINE config 2
@@ -107,9 +111,11 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+HOST_THREADS = os.cpu_count() or 1   # torchrun exports OMP_NUM_THREADS=1; the CPU arm asks for every core explicitly
+
+
 def _oracle_threads():
-    from oracle import oracle as O
-    return O.num_threads()
+    return HOST_THREADS
 
 
 def cpu_loss_baseline(pred_np, target_np, budget_s=10.0, max_images=None):
@@ -118,11 +124,11 @@ def cpu_loss_baseline(pred_np, target_np, budget_s=10.0, max_images=None):
     n = pred_np.shape[0] if max_images is None else min(max_images, pred_np.shape[0])
     p, t = pred_np[:n], target_np[:n]
     S = p.shape[1]
-    O.loss(p[:64], t[:64], batch_size=n)      # build/load + warm
+    O.loss(p[:64], t[:64], batch_size=n, nthreads=HOST_THREADS)      # build/load + warm
     t0 = time.perf_counter()
     passes = 0
     while True:
-        O.loss(p, t, batch_size=n)
+        O.loss(p, t, batch_size=n, nthreads=HOST_THREADS)
         passes += 1
         el = time.perf_counter() - t0
         if el >= budget_s or passes >= 50:
@@ -135,11 +141,11 @@ def cpu_loss_baseline(pred_np, target_np, budget_s=10.0, max_images=None):
 def cpu_decode_baseline(pred_np, budget_s=8.0):
     from oracle import oracle as O
     n = pred_np.shape[0]
-    O.decode_nms(pred_np[:8], thresh=DEC_THRESH, nms_th=DEC_IOU)
+    O.decode_nms(pred_np[:8], thresh=DEC_THRESH, nms_th=DEC_IOU, nthreads=HOST_THREADS)
     t0 = time.perf_counter()
     passes = 0
     while True:
-        O.decode_nms(pred_np, thresh=DEC_THRESH, nms_th=DEC_IOU)
+        O.decode_nms(pred_np, thresh=DEC_THRESH, nms_th=DEC_IOU, nthreads=HOST_THREADS)
         passes += 1
         el = time.perf_counter() - t0
         if el >= budget_s or passes >= 50:
@@ -161,22 +167,22 @@ def run_reference(args, rank, world):
     pred, target = synth.make_loss_inputs(n, S_LOSS, seed=SEED + 3000)
     p, t = pred.numpy(), target.numpy()
     for _ in range(max(args.warmup, 1)):
-        O.loss(p, t, batch_size=n)
+        O.loss(p, t, batch_size=n, nthreads=HOST_THREADS)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.loss(p, t, batch_size=n)
+        O.loss(p, t, batch_size=n, nthreads=HOST_THREADS)
     el = time.perf_counter() - t0
     cells = n * S_LOSS * S_LOSS
     value = cells * args.steps / el
     dp, _ = synth.make_tie_free_decode_inputs(N_DEC, S_DEC, seed=2)
     dnp = dp.numpy()
-    O.decode_nms(dnp, thresh=DEC_THRESH, nms_th=DEC_IOU)
+    O.decode_nms(dnp, thresh=DEC_THRESH, nms_th=DEC_IOU, nthreads=HOST_THREADS)
     t1 = time.perf_counter()
     dsteps = max(1, min(args.steps, 20))
     for _ in range(dsteps):
-        O.decode_nms(dnp, thresh=DEC_THRESH, nms_th=DEC_IOU)
+        O.decode_nms(dnp, thresh=DEC_THRESH, nms_th=DEC_IOU, nthreads=HOST_THREADS)
     dval = N_DEC * dsteps / (time.perf_counter() - t1)
-    cores = O.num_threads()
+    cores = HOST_THREADS
     sample = "each step = loss+grad over %d images (%d cells) of config 3, OpenMP x%d" % (n, cells, cores)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
@@ -226,6 +232,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL would print its version banner on stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=dev)
     hbm_peak, sm_max_mhz, peak_src = _peaks()
 
