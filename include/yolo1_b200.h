@@ -139,6 +139,14 @@ YOLO1_API int yolo1_decode_nms(const void* pred, const int64_t pred_strides[4], 
                      float* out_boxes, float* out_scores, int32_t* out_cls, int32_t* out_counts,
                      int32_t* keep_idx, int32_t* cand_counts, void* stream);
 
+/*
+ * Post-processing of run_test_mAP (utils/utils.py:406-407 `bboxes.clamp(0,1)` and bbox_un_norm :347-354):
+ * pixels[k] = (int)(clamp(boxes[k], 0, 1) * {img_w, img_h, img_w, img_h}) -- fp32 multiply, truncation --
+ * for n_boxes xyxy boxes (boxes and pixels 16-byte aligned; int32 [n_boxes,4]).
+ */
+YOLO1_API int yolo1_boxes_to_pixels(const float* boxes, int64_t n_boxes, float img_w, float img_h, int32_t* pixels,
+                                    void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points: the same path for callers that hold HOST memory (the reference's callers
  * hold CPU tensors when run as shipped with device='cpu').  A context owns the device staging

@@ -245,7 +245,9 @@ def gen_map(meta):
     synthetic GT built from perturbed top detections."""
     S = 7
     pred, _ = synth.make_tie_free_decode_inputs(96, S, seed=41)
-    rng = np.random.RandomState(5)
+    pred_in = pred.numpy().copy()   # the reference decoder overwrites x,y of candidate boxes IN PLACE
+    rng = np.random.RandomState(5)  # (utils/utils.py:119,123): keep what the network "produced"
+
     gt = {}
     for n in range(pred.shape[0]):
         b, c, s = ref_decoder(pred[n], S, 0.005, 0.45)
@@ -255,13 +257,14 @@ def gen_map(meta):
             if box[2] <= box[0] or box[3] <= box[1]:
                 continue
             gt.setdefault(("img%04d" % n, U.VOC_CLASSES[int(c[k])]), []).append(box)
-    dataset = [(pred[n], torch.zeros(1), "/x/img%04d.jpg" % n) for n in range(pred.shape[0])]
+    dataset = [(pred[n].clone(), torch.zeros(1), "/x/img%04d.jpg" % n) for n in range(pred.shape[0])]
     buf = io.StringIO()
     with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(io.StringIO()):
         m = U.run_test_mAP(lambda x: x, copy.deepcopy(gt), dataset, len(dataset), S=S, device="cpu")
     aps = [float(l.split(" ap ")[1].rstrip("-")) for l in buf.getvalue().splitlines() if "---class" in l]
     print("synthetic mAP case: mAP=%r over %d classes" % (m, len(aps)))
-    np.savez_compressed(os.path.join(GOLD, "map_case.npz"), pred=pred.numpy())
+    assert np.array_equal(pred.numpy(), pred_in)
+    np.savez_compressed(os.path.join(GOLD, "map_case.npz"), pred=pred_in)
     meta["map_case"] = dict(S=S, mAP=m, aps=aps, gt=[[k[0], k[1], v] for k, v in sorted(gt.items())])
 
 

@@ -38,6 +38,7 @@ SIGNATURES = {
                              _vp, _vp, _vp]),
     "yolo1_decode_nms": (_c.c_int, [_vp, _i64p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int,
                                     _c.c_double, _c.c_float, _c.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "yolo1_boxes_to_pixels": (_c.c_int, [_vp, _c.c_int64, _c.c_float, _c.c_float, _vp, _vp]),
     "yolo1_host_ctx_create": (_c.c_int, [_c.POINTER(_vp), _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int64]),
     "yolo1_host_ctx_destroy": (None, [_vp]),
     "yolo1_host_pin": (_c.c_int, [_vp, _c.c_size_t]),

@@ -4,7 +4,4 @@ the reference's drawing / logging / dataset helpers stay in the reference tree. 
 from yolo_v1_b200.decode import (decoder, nms, compute_iou_matrix, convert_CxCyWH_to_X1Y1X2Y2,  # noqa: F401
                                  decode_nms_batched)
 
-# class-name table the callers index with the returned class ids (reference utils/utils.py:187-192)
-VOC_CLASSES = ('aeroplane', 'bicycle', 'bird', 'boat', 'bottle', 'bus', 'car', 'cat', 'chair', 'cow',
-               'diningtable', 'dog', 'horse', 'motorbike', 'person', 'pottedplant', 'sheep', 'sofa', 'train',
-               'tvmonitor')
+from yolo_v1_b200.voc import VOC_CLASSES, voc_ap, voc_eval, run_test_mAP  # noqa: F401

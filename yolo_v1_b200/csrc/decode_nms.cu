@@ -316,6 +316,19 @@ __global__ void nms_kernel(const __grid_constant__ DecodeParams p) {
   if (threadIdx.x == 0) p.out_counts[n] = kept;
 }
 
+// run_test_mAP post-processing (utils/utils.py:406-407, :347-354): clamp to [0,1], scale to pixels in fp32,
+// truncate toward zero.  One thread per box (float4 in, int4 out).
+__global__ void __launch_bounds__(256) boxes_to_pixels_kernel(const float4* __restrict__ boxes, int64_t n,
+                                                              float w, float h, int4* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float4 b = boxes[i];
+    b.x = fminf(fmaxf(b.x, 0.f), 1.f), b.y = fminf(fmaxf(b.y, 0.f), 1.f);
+    b.z = fminf(fmaxf(b.z, 0.f), 1.f), b.w = fminf(fmaxf(b.w, 0.f), 1.f);
+    out[i] = make_int4((int)(b.x * w), (int)(b.y * h), (int)(b.z * w), (int)(b.w * h));
+  }
+}
+
 int block_threads(int max_n) { return max_n <= 128 ? 128 : 256; }
 
 template <typename K>
@@ -387,6 +400,19 @@ int yolo1_nms(const float* boxes, const float* scores, const int32_t* cls, const
   p.keep = keep, p.out_counts = keep_counts;
   p.max_n = max_n, p.iou_thr = iou_thr, p.per_class = per_class ? 1 : 0;
   return launch(nms_kernel, p, N, 0, (cudaStream_t)stream);
+}
+
+int yolo1_boxes_to_pixels(const float* boxes, int64_t n_boxes, float img_w, float img_h, int32_t* pixels,
+                          void* stream) {
+  if (n_boxes < 0) return YOLO1_ERR_ARG;
+  if (n_boxes == 0) return 0;
+  if (!boxes || !pixels) return YOLO1_ERR_ARG;
+  if ((uintptr_t)boxes % 16 || (uintptr_t)pixels % 16) return YOLO1_ERR_ALIGN;
+  int64_t grid = (n_boxes + 255) / 256;
+  if (grid > yolo1::kNumSMs * 16) grid = yolo1::kNumSMs * 16;
+  yolo1::boxes_to_pixels_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(boxes), n_boxes, img_w, img_h, reinterpret_cast<int4*>(pixels));
+  return (int)cudaGetLastError();
 }
 
 int yolo1_decode_nms(const void* pred, const int64_t pred_strides[4], int pred_dtype, int64_t N, int S, int B,
