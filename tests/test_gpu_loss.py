@@ -17,7 +17,7 @@ from yolo_v1_b200 import synth
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, -1]   # launch shapes of the streaming kernel; -1 = strided kernel
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, -1]   # launch shapes of the streaming kernel; -1 = strided kernel
 
 
 def _y():
@@ -100,6 +100,30 @@ def test_permuted_nchw_view_is_read_in_place():
     view.copy_(pred)
     _, grad, terms = y.yolo_loss_fused(view, target.cuda(), batch_size=50)
     _check(terms, grad, o_terms, o_grad, "unaligned")
+
+
+@pytest.mark.parametrize("S,N", [(7, 1), (7, 3), (7, 4), (7, 67), (14, 1), (14, 33), (3, 50), (16, 5), (17, 3)])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_planar_fast_path_all_shapes(S, N, dtype):
+    """Channel-planar pred/grad (the backbone's view): whole-image tiles through the copy engine, image tails
+    through the strided path, grids that do not fit a 256-cell tile (S=17) through the strided kernel."""
+    y = _y()
+    pred, target = synth.make_loss_inputs(N, S, seed=900 + S + N, p_obj=0.2, variant="mixed")
+    if dtype == "bf16":
+        pred = pred.to(torch.bfloat16)
+    o_terms, o_grad = O.loss(pred.float().numpy(), target.numpy(), batch_size=N)
+    planar = pred.cuda().permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+    for variant in (0, 1):
+        _, grad, terms = y.yolo_loss_fused(planar, target.cuda(), batch_size=N, variant=variant)
+        assert grad.stride() == planar.stride()
+        if dtype == "f32":
+            _check(terms, grad, o_terms, o_grad, ("planar", S, N, variant))
+        else:
+            _check(terms, None, o_terms, None, ("planar bf16", S, N, variant))
+            g = grad.float().cpu().numpy()
+            assert np.all(np.abs(g - o_grad) <= np.abs(o_grad) * 2.0 ** -8 + 1e-30)
+        _, _, t2 = y.yolo_loss_fused(planar, target.cuda(), batch_size=N, variant=variant, want_grad=False)
+        assert torch.equal(t2, terms)
 
 
 def test_batch_size_divisor_lambdas_and_paper_mode():

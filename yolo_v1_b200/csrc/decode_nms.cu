@@ -14,6 +14,9 @@
 //   sweep  : one warp walks the sorted boxes word by word; lane w holds word w of the removed-set; a kept
 //            box ORs its row in.  A suppressed box never suppresses (iterated semantics of the reference).
 //   store  : kept detections in descending score order (float4 boxes), counts.
+#include <math.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace yolo1 {
@@ -29,6 +32,12 @@ struct DecodeParams {
   double thresh;  // python double, utils/utils.py:129
   float iou_thr;
   int per_class;
+  // division-free form of `fl32(inter / u) <= thr` (see set_threshold): thr_mid = midpoint between thr and the
+  // next float above it (exact in double); thr_tie_ok = 1 when that midpoint itself rounds down to thr
+  // (round-to-nearest-even); thr_fast = 0 when thr is outside the range where the shortcut is proven.
+  double thr_mid;
+  int thr_tie_ok;
+  int thr_fast;
   // decode outputs / nms inputs
   float* boxes;
   float* scores;
@@ -174,7 +183,22 @@ __device__ __forceinline__ int decode_phase(const DecodeParams& p, const Smem& s
 }
 
 // ---- phase: rank sort + suppression matrix + sweep (utils/utils.py:150-184).  Returns kept count. --------
-__device__ __forceinline__ int nms_phase(const Smem& sm, int n, float thr, int per_class) {
+// `!(fl32(inter / u) <= thr)` without the division.  fl32() is monotone, so fl32(x) <= thr  <=>  x < mid, or
+// x == mid when mid rounds to thr, where mid is the midpoint between thr and its successor.  For u > 0 that is
+// inter < mid * u; inter and u carry 24 significant bits and mid 25, so the product is exact in double.
+// Operands outside the proven range (u <= 0, non-finite, NaN, odd thresholds) take the real IEEE division.
+__device__ __forceinline__ bool iou_exceeds(float inter, float u, const DecodeParams& p) {
+  if (p.thr_fast && u > 0.f && u < 3.0e38f && inter >= 0.f && inter < 3.0e38f) {
+    const double lhs = (double)inter, rhs = p.thr_mid * (double)u;
+    return !(lhs < rhs || (p.thr_tie_ok && lhs == rhs));
+  }
+  return !(inter / u <= p.iou_thr);
+}
+
+__device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodeParams& p) {
+  const float thr = p.iou_thr;
+  const int per_class = p.per_class;
+  (void)thr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int W = (n + 31) >> 5;
   // :161 order = scores descending; ties -> lower emission index first (canonical)
@@ -191,28 +215,31 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, float thr, int p
     sm.sidx[rank] = k;
   }
   __syncthreads();
-  // suppression matrix: row i, bit j (j > i) set iff box j dies when box i is kept (:166-180)
-  for (int item = warp; item < n * W; item += nwarps) {
-    const int i = item / W, w = item - i * W;
-    if (w < (i >> 5)) continue;  // columns before i are never consulted
-    const int j = (w << 5) + lane;
-    bool dead = false;
-    if (j > i && j < n) {
-      const float4 A = sm.sbox[i], Bx = sm.sbox[j];
-      const float xx1 = Bx.x < A.x ? A.x : Bx.x;  // clamp(min=x1[i])
-      const float yy1 = Bx.y < A.y ? A.y : Bx.y;
-      const float xx2 = Bx.z > A.z ? A.z : Bx.z;  // clamp(max=x2[i])
-      const float yy2 = Bx.w > A.w ? A.w : Bx.w;
-      float ww = xx2 - xx1, hh = yy2 - yy1;
-      if (ww < 0.f) ww = 0.f;
-      if (hh < 0.f) hh = 0.f;
-      const float inter = ww * hh;
-      const float ovr = inter / ((sm.sarea[i] + sm.sarea[j]) - inter);
-      dead = !(ovr <= thr);
-      if (per_class && sm.cls[sm.sidx[i]] != sm.cls[sm.sidx[j]]) dead = false;
+  // suppression matrix: row i, bit j (j > i) set iff box j dies when box i is kept (:166-180).
+  // A warp takes a row, then walks the words at or after the diagonal (columns before i are never consulted).
+  for (int i = warp; i < n; i += nwarps) {
+    const float4 A = sm.sbox[i];
+    const float area_i = sm.sarea[i];
+    const int cls_i = per_class ? sm.cls[sm.sidx[i]] : 0;
+    for (int w = i >> 5; w < W; ++w) {
+      const int j = (w << 5) + lane;
+      bool dead = false;
+      if (j > i && j < n) {
+        const float4 Bx = sm.sbox[j];
+        const float xx1 = Bx.x < A.x ? A.x : Bx.x;  // clamp(min=x1[i])
+        const float yy1 = Bx.y < A.y ? A.y : Bx.y;
+        const float xx2 = Bx.z > A.z ? A.z : Bx.z;  // clamp(max=x2[i])
+        const float yy2 = Bx.w > A.w ? A.w : Bx.w;
+        float ww = xx2 - xx1, hh = yy2 - yy1;
+        if (ww < 0.f) ww = 0.f;
+        if (hh < 0.f) hh = 0.f;
+        const float inter = ww * hh;
+        dead = iou_exceeds(inter, (area_i + sm.sarea[j]) - inter, p);   // ovr = inter / (a_i + a_j - inter)
+        if (per_class && cls_i != sm.cls[sm.sidx[j]]) dead = false;
+      }
+      const unsigned bits = __ballot_sync(0xffffffffu, dead);
+      if (lane == 0) sm.mask[i * W + w] = bits;
     }
-    const unsigned bits = __ballot_sync(0xffffffffu, dead);
-    if (lane == 0) sm.mask[item] = bits;
   }
   __syncthreads();
   // sweep: warp 0; lane w owns word w of the removed set (n <= 1024 -> W <= 32)
@@ -249,7 +276,7 @@ __global__ void decode_nms_kernel(const __grid_constant__ DecodeParams p) {
   load_image<E>(p, n, sm.img);
   __syncthreads();
   const int cand = decode_phase(p, sm);
-  const int kept = cand > 0 ? nms_phase(sm, cand, p.iou_thr, p.per_class) : 0;
+  const int kept = cand > 0 ? nms_phase(sm, cand, p) : 0;
   for (int t = threadIdx.x; t < kept; t += blockDim.x) {
     const int src = sm.keep[t], e = sm.sidx[src];
     const int64_t dst = n * p.max_n + t;
@@ -310,7 +337,7 @@ __global__ void nms_kernel(const __grid_constant__ DecodeParams p) {
     sm.cls[t] = p.cls ? p.cls[src] : 0;
   }
   __syncthreads();
-  const int kept = cnt > 0 ? nms_phase(sm, cnt, p.iou_thr, p.per_class) : 0;
+  const int kept = cnt > 0 ? nms_phase(sm, cnt, p) : 0;
   for (int t = threadIdx.x; t < p.max_n; t += blockDim.x)
     p.keep[n * p.max_n + t] = t < kept ? sm.sidx[sm.keep[t]] : 0;
   if (threadIdx.x == 0) p.out_counts[n] = kept;
@@ -349,6 +376,20 @@ int check_decode_args(const void* pred, const int64_t st[4], int dtype, int64_t 
   if ((int64_t)S * S * B > kMaxCand || 5 * B + C > 128) return YOLO1_ERR_UNSUPPORTED;
   if ((uintptr_t)pred % (dtype == YOLO1_DTYPE_F32 ? 4 : 2)) return YOLO1_ERR_ALIGN;
   return 0;
+}
+
+// Precompute the division-free threshold test (iou_exceeds).  Proven for finite 0 <= thr < 2^100.
+void set_threshold(DecodeParams& p, float thr) {
+  p.iou_thr = thr;
+  p.thr_fast = (thr >= 0.f && thr < 1.0e30f) ? 1 : 0;
+  p.thr_mid = 0.0, p.thr_tie_ok = 0;
+  if (p.thr_fast) {
+    const float up = nextafterf(thr, INFINITY);
+    p.thr_mid = 0.5 * ((double)thr + (double)up);
+    uint32_t bits;
+    memcpy(&bits, &thr, 4);
+    p.thr_tie_ok = (bits & 1u) == 0u;   // ties round to the even mantissa
+  }
 }
 
 void fill_decode(DecodeParams& p, const void* pred, const int64_t st[4], int S, int B, int C, double thresh) {
@@ -398,7 +439,8 @@ int yolo1_nms(const float* boxes, const float* scores, const int32_t* cls, const
   p.boxes = const_cast<float*>(boxes), p.scores = const_cast<float*>(scores), p.cls = const_cast<int32_t*>(cls);
   p.counts = const_cast<int32_t*>(counts);
   p.keep = keep, p.out_counts = keep_counts;
-  p.max_n = max_n, p.iou_thr = iou_thr, p.per_class = per_class ? 1 : 0;
+  p.max_n = max_n, p.per_class = per_class ? 1 : 0;
+  set_threshold(p, iou_thr);
   return launch(nms_kernel, p, N, 0, (cudaStream_t)stream);
 }
 
@@ -430,7 +472,8 @@ int yolo1_decode_nms(const void* pred, const int64_t pred_strides[4], int pred_d
     return YOLO1_ERR_ALIGN;
   DecodeParams p;
   fill_decode(p, pred, pred_strides, S, B, C, thresh);
-  p.iou_thr = iou_thr, p.per_class = per_class ? 1 : 0;
+  p.per_class = per_class ? 1 : 0;
+  set_threshold(p, iou_thr);
   p.out_boxes = out_boxes, p.out_scores = out_scores, p.out_cls = out_cls, p.out_counts = out_counts;
   p.keep = keep_idx, p.cand_counts = cand_counts;
   const int img = S * S * (5 * B + C);

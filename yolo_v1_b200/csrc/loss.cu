@@ -173,6 +173,26 @@ struct GlobOut {
   __device__ __forceinline__ void st(int c, float v) const { st_elem(p + c * cs, v); }
 };
 
+// channel-planar tile in shared memory: channel c of a cell lives `plane` elements apart (lanes <-> consecutive
+// cells, so 32-bit accesses are conflict-free)
+template <typename E>
+struct PlanarIn {
+  const E* p;
+  int plane;
+  __device__ __forceinline__ float2 ld2(int c) const {
+    return make_float2(ld_elem(p + c * plane), ld_elem(p + (c + 1) * plane));
+  }
+};
+template <typename E>
+struct PlanarOut {
+  E* p;
+  int plane;
+  __device__ __forceinline__ void st2(int c, float x, float y) const {
+    st_elem(p + c * plane, x);
+    st_elem(p + (c + 1) * plane, y);
+  }
+};
+
 // ---- fast cell: B = 2, C = 20, channel pairs (conflict-free 64-bit shared accesses) -----------------
 // Returns true when the cell holds an object (target channel 0 == 1, v1Loss.py:28).
 template <bool HAS_GRAD, typename PA, typename TA, typename GA>
@@ -460,7 +480,8 @@ __global__ void __launch_bounds__(TILE) loss_tma_kernel(const __grid_constant__ 
   constexpr int D = 30;
   constexpr uint32_t PB = TILE * D * sizeof(E), TB = TILE * D * sizeof(float), GB = PB;
   static_assert(PB % 16 == 0 && TB % 16 == 0, "bulk copies move multiples of 16 bytes");
-  static_assert(NOUT >= 2, "need at least two output buffers");
+  static_assert(NOUT == 0 || NOUT >= 2, "NOUT = 0: gradient tile overwrites the pred stage in place; else >= 2 buffers");
+  constexpr bool INPLACE = NOUT == 0;
   extern __shared__ __align__(128) unsigned char smem[];
   E* sp = reinterpret_cast<E*>(smem);
   float* st = reinterpret_cast<float*>(smem + STAGES * PB);
@@ -495,24 +516,29 @@ __global__ void __launch_bounds__(TILE) loss_tma_kernel(const __grid_constant__ 
   using PIn = typename SmemIn<E>::type;
   using GOut = typename SmemOut<E>::type;
   for (int64_t k = 0; k < my_n; ++k) {
-    const int s = (int)(k % STAGES), o = (int)(k % NOUT);
+    const int s = (int)(k % STAGES), o = INPLACE ? 0 : (int)(k % (NOUT > 0 ? NOUT : 1));
     mbar_wait(&bars[s], (uint32_t)((k / STAGES) & 1));
     const PIn P{sp + s * (TILE * D) + tid * D};
     const SmemInF32 T{st + s * (TILE * D) + tid * D};
-    const GOut G{so + o * (TILE * D) + tid * D};
+    // in-place: every thread reads its own cell's 30 values before it overwrites them with the gradient
+    E* gtile = INPLACE ? sp + s * (TILE * D) : so + o * (TILE * D);
+    const GOut G{gtile + tid * D};
     if (cell_b2c20<HAS_GRAD>(P, T, G, p, sums))
       note_object(m1, m2, ((int64_t)blockIdx.x + k * gridDim.x) * TILE + tid);
     if (HAS_GRAD) {
       fence_async_smem();  // my shared-memory gradient writes -> visible to the copy engine
-      if (tid == 0) bulk_wait_read<NOUT - 2>();  // buffer (k+1) % NOUT is no longer being read
+      if (!INPLACE && tid == 0) bulk_wait_read<(NOUT >= 2 ? NOUT - 2 : 0)>();  // buffer (k+1) % NOUT is free again
     }
     __syncthreads();
     if (tid == 0) {
       if (HAS_GRAD) {
-        bulk_s2g(gg + ((int64_t)blockIdx.x + k * gridDim.x) * (TILE * D), so + o * (TILE * D), GB, pol);
+        bulk_s2g(gg + ((int64_t)blockIdx.x + k * gridDim.x) * (TILE * D), gtile, GB, pol);
         bulk_commit();
       }
-      if (k + STAGES < my_n) issue(k + STAGES);
+      if (k + STAGES < my_n) {
+        if (HAS_GRAD && INPLACE) bulk_wait_read<0>();  // the store has drained stage s: it may be refilled
+        issue(k + STAGES);
+      }
     }
   }
   // ragged tail (< TILE cells): one CTA, straight from / to global memory
@@ -522,6 +548,91 @@ __global__ void __launch_bounds__(TILE) loss_tma_kernel(const __grid_constant__ 
     const GlobIn<E> P{gp + q * D, 1};
     const GlobIn<float> T{p.target + q * D, 1};
     const GlobOut<E> G{HAS_GRAD ? gg + q * D : nullptr, 1};
+    if (cell_generic<HAS_GRAD, false>(P, T, G, p, sums)) note_object(m1, m2, q);
+  }
+  block_epilogue<E, HAS_GRAD, true>(sums, m1, m2, p);
+}
+
+// ---- K1 fast kernel, channel-planar pred/grad: the backbone's permuted NCHW view (OriginResNet.py:189) ------
+// pred / grad are [N][30][S*S] in memory (element strides (30 S^2, S, 1, S^2)), target is contiguous NHWC.
+// An image's 30 planes are one contiguous block, so a tile of `tile_imgs` whole images still moves with one
+// bulk copy per tensor; one thread per cell reads its channels S*S elements apart (conflict-free) and writes
+// the gradient tile in the same planar layout, so `permute`'s backward stays a free view.
+template <typename E, bool HAS_GRAD, int STAGES, int NOUT>
+__global__ void __launch_bounds__(256) loss_tma_planar_kernel(const __grid_constant__ LossParams p, int tile_imgs) {
+  constexpr int D = 30;
+  const int SS = p.S * p.S, tile_cells = tile_imgs * SS, tile_elems = tile_cells * D;
+  const uint32_t PB = tile_elems * sizeof(E), TB = tile_elems * sizeof(float), GB = PB;
+  extern __shared__ __align__(128) unsigned char smem[];
+  E* sp = reinterpret_cast<E*>(smem);
+  float* st = reinterpret_cast<float*>(smem + STAGES * PB);
+  E* so = reinterpret_cast<E*>(smem + STAGES * (PB + TB));   // NOUT == 0: the gradient overwrites the pred stage
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (PB + TB) + NOUT * GB);
+  constexpr bool INPLACE = NOUT == 0;
+
+  const int tid = threadIdx.x;
+  const int64_t n_imgs = p.cells / SS;
+  const int64_t full = n_imgs / tile_imgs;
+  const int64_t my_n = full > (int64_t)blockIdx.x ? (full - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const E* gp = reinterpret_cast<const E*>(p.pred);
+  E* gg = reinterpret_cast<E*>(p.grad);
+  uint64_t pol = 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+    pol = policy_evict_first();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t k) {
+    const int s = (int)(k % STAGES);
+    const int64_t off = ((int64_t)blockIdx.x + k * gridDim.x) * tile_elems;
+    mbar_arrive_expect_tx(&bars[s], PB + TB);
+    bulk_g2s(sp + s * tile_elems, gp + off, PB, &bars[s], pol);
+    bulk_g2s(st + s * tile_elems, p.target + off, TB, &bars[s], pol);
+  };
+  if (tid == 0)
+    for (int64_t k = 0; k < my_n && k < STAGES; ++k) issue(k);
+
+  CellSums sums = {0.f, 0.f, 0.f, 0.f};
+  uint32_t m1 = 0, m2 = 0;
+  const int img = tid / SS, r = tid - img * SS;   // my cell inside a tile
+  const int poff = img * (D * SS) + r;
+  for (int64_t k = 0; k < my_n; ++k) {
+    const int s = (int)(k % STAGES);
+    mbar_wait(&bars[s], (uint32_t)((k / STAGES) & 1));
+    // in place: a thread reads its cell's 30 values before it overwrites them with the gradient
+    E* gtile = INPLACE ? sp + s * tile_elems : so + (int)(k % (NOUT > 0 ? NOUT : 1)) * tile_elems;
+    if (tid < tile_cells) {
+      const PlanarIn<E> P{sp + s * tile_elems + poff, SS};
+      const SmemInF32 T{st + s * tile_elems + tid * D};
+      const PlanarOut<E> G{gtile + poff, SS};
+      if (cell_b2c20<HAS_GRAD>(P, T, G, p, sums))
+        note_object(m1, m2, ((int64_t)blockIdx.x + k * gridDim.x) * tile_cells + tid);
+    }
+    if (HAS_GRAD) {
+      fence_async_smem();
+      if (!INPLACE && tid == 0) bulk_wait_read<(NOUT >= 2 ? NOUT - 2 : 0)>();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (HAS_GRAD) {
+        bulk_s2g(gg + ((int64_t)blockIdx.x + k * gridDim.x) * tile_elems, gtile, GB, pol);
+        bulk_commit();
+      }
+      if (k + STAGES < my_n) {
+        if (HAS_GRAD && INPLACE) bulk_wait_read<0>();  // the store has drained stage s: it may be refilled
+        issue(k + STAGES);
+      }
+    }
+  }
+  // ragged tail (< tile_imgs images): one CTA, strided global accesses
+  const int64_t tail0 = full * tile_cells;
+  if ((int64_t)blockIdx.x == full % gridDim.x && tail0 + tid < p.cells && tid < tile_cells) {
+    const int64_t q = tail0 + tid;
+    const GlobIn<E> P{gp + cell_offset<E>(p.ps, q, p.S), p.ps[3]};
+    const GlobIn<float> T{p.target + cell_offset<float>(p.ts, q, p.S), p.ts[3]};
+    const GlobOut<E> G{HAS_GRAD ? gg + cell_offset<E>(p.gs, q, p.S) : nullptr, p.gs[3]};
     if (cell_generic<HAS_GRAD, false>(P, T, G, p, sums)) note_object(m1, m2, q);
   }
   block_epilogue<E, HAS_GRAD, true>(sums, m1, m2, p);
@@ -601,8 +712,66 @@ int launch_tma_variant(const LossParams& p, int variant, cudaStream_t stream) {
     case 5: return launch_tma<E, HAS_GRAD, 256, 2, 2>(p, stream);
     case 6: return launch_tma<E, HAS_GRAD, 32, 4, 2>(p, stream);
     case 7: return launch_tma<E, HAS_GRAD, 32, 6, 3>(p, stream);
+    case 8: return launch_tma<E, HAS_GRAD, 128, 2, 0>(p, stream);   // in-place gradient tile: 61 KB, 3 CTAs/SM
+    case 9: return launch_tma<E, HAS_GRAD, 128, 3, 0>(p, stream);   // 92 KB, 2 CTAs/SM
+    case 10: return launch_tma<E, HAS_GRAD, 192, 2, 0>(p, stream);  // 92 KB, 2 CTAs/SM
+    case 11: return launch_tma<E, HAS_GRAD, 96, 2, 0>(p, stream);   // 46 KB, 4 CTAs/SM
+    case 12: return launch_tma<E, HAS_GRAD, 64, 2, 0>(p, stream);   // 31 KB, 7 CTAs/SM
+    case 13: return launch_tma<E, HAS_GRAD, 256, 2, 0>(p, stream);  // 123 KB, 1 CTA/SM
     default: return YOLO1_ERR_ARG;
   }
+}
+
+bool planar(const int64_t st[4], int S, int D) {
+  return st[3] == (int64_t)S * S && st[2] == 1 && st[1] == S && st[0] == (int64_t)S * S * D;
+}
+
+// whole images per tile so that both tiles are multiples of 16 bytes and hold 128..256 cells; 0 = no fit
+int planar_tile_imgs(int S, size_t esz, int target_cells) {
+  const int SS = S * S;
+  int m = 0;
+  for (int k = 1; k <= 16; ++k)
+    if (((size_t)k * SS * 30 * esz) % 16 == 0 && ((size_t)k * SS * 120) % 16 == 0) {
+      m = k;
+      break;
+    }
+  if (m == 0 || m * SS > 256) return 0;
+  int t = m;
+  while ((t + m) * SS <= target_cells) t += m;
+  return t;
+}
+
+template <typename E, bool HAS_GRAD, int NOUT>
+int launch_planar_n(const LossParams& p, int tile_imgs, cudaStream_t stream) {
+  constexpr int STAGES = 2;
+  const int tile_cells = tile_imgs * p.S * p.S;
+  const size_t smem = (size_t)STAGES * tile_cells * 30 * (sizeof(E) + 4) + (size_t)NOUT * tile_cells * 30 * sizeof(E) +
+                      STAGES * sizeof(uint64_t);
+  const int threads = (tile_cells + 31) / 32 * 32;
+  auto kern = loss_tma_planar_kernel<E, HAS_GRAD, STAGES, NOUT>;
+  YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = kNumSMs, per_sm = 1;
+  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
+  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  YOLO1_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t tiles = p.cells / tile_cells;
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > tiles) grid = tiles;
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, threads, smem, stream>>>(p, tile_imgs);
+  return (int)cudaGetLastError();
+}
+
+// Two CTAs per SM are what keeps the copy engine busy (tools/tune_loss.py): separate output buffers while the
+// tile is small enough for that (<= 110 KB per CTA), gradient written in place over the pred stage otherwise.
+template <typename E, bool HAS_GRAD>
+int launch_planar(const LossParams& p, int tile_imgs, cudaStream_t stream) {
+  const size_t tile_cells = (size_t)tile_imgs * p.S * p.S;
+  const size_t separate = 2 * tile_cells * 30 * (sizeof(E) + 4) + 2 * tile_cells * 30 * sizeof(E);
+  if (separate <= 110 * 1024) return launch_planar_n<E, HAS_GRAD, 2>(p, tile_imgs, stream);
+  return launch_planar_n<E, HAS_GRAD, 0>(p, tile_imgs, stream);
 }
 
 template <typename E, bool HAS_GRAD>
@@ -663,6 +832,15 @@ int loss_launch_chunk(const void* pred, const int64_t ps[4], int pred_dtype, con
                         : launch_tma_variant<__nv_bfloat16, false>(p, variant, stream);
     return grad ? launch_tma_variant<float, true>(p, variant, stream)
                 : launch_tma_variant<float, false>(p, variant, stream);
+  }
+  const int tile_imgs = planar_tile_imgs(S, esz, variant == 1 ? 224 : 128);
+  const bool fast_planar = variant >= 0 && B == 2 && C == 20 && tile_imgs > 0 && planar(ps, S, D) &&
+                           contiguous(ts, S, D) && (!grad || planar(gs, S, D)) && (uintptr_t)pred % 16 == 0 &&
+                           (uintptr_t)target % 16 == 0 && (!grad || (uintptr_t)grad % 16 == 0);
+  if (fast_planar) {
+    if (bf) return grad ? launch_planar<__nv_bfloat16, true>(p, tile_imgs, stream)
+                        : launch_planar<__nv_bfloat16, false>(p, tile_imgs, stream);
+    return grad ? launch_planar<float, true>(p, tile_imgs, stream) : launch_planar<float, false>(p, tile_imgs, stream);
   }
   if (bf) return grad ? launch_generic<__nv_bfloat16, true>(p, stream) : launch_generic<__nv_bfloat16, false>(p, stream);
   return grad ? launch_generic<float, true>(p, stream) : launch_generic<float, false>(p, stream);
