@@ -160,6 +160,17 @@ typedef struct yolo1_host_ctx yolo1_host_ctx;
 YOLO1_API int yolo1_host_ctx_create(yolo1_host_ctx** ctx, int device, int S, int B, int C, int64_t chunk_images);
 YOLO1_API void yolo1_host_ctx_destroy(yolo1_host_ctx* ctx);
 
+/*
+ * Loss calls whose pred/target/grad buffers are pinned AND device-mapped (cudaHostAlloc, torch pin_memory(),
+ * yolo1_host_pin) can be served without staging copies: the kernel reads the bytes it needs (one 32-byte
+ * sector of target and of pred per cell; the full 240 B only for object cells) straight from host memory and
+ * bulk-stores the gradient straight into the caller's buffer.  mode 2 (default): everything in place, one
+ * launch.  mode 1: target streamed by the copy engine chunk by chunk, pred / grad in place.  mode 3: target up
+ * and gradient down by the copy engines, only pred in place.  mode 0: the staged H2D / kernel / D2H pipeline
+ * (always used for pageable memory).  All modes give the same results; measured rates are in DESIGN.md.
+ */
+YOLO1_API int yolo1_host_ctx_set_zero_copy(yolo1_host_ctx* ctx, int enable);
+
 /* Register / unregister caller memory as pinned (cudaHostRegister) so the copies run at full PCIe rate. */
 YOLO1_API int yolo1_host_pin(void* ptr, size_t bytes);
 YOLO1_API int yolo1_host_unpin(void* ptr);

@@ -248,14 +248,39 @@ def test_host_buffer_path_equals_device_path_and_spans_chunks():
         ctx = y.HostContext(S, chunk_images=chunk)
         terms, grad = ctx.loss(pred, target, batch_size=N)
         _check(terms, grad, o_terms, o_grad, ("host", chunk))
-        t2, g2 = ctx.loss(pred.pin_memory(), target.pin_memory(), batch_size=N, want_grad=False)
-        assert g2 is None and torch.equal(t2, terms)
+        # pinned + mapped buffers: the zero-copy kernel reads / writes host memory in place; staged path forced too
+        pp, tp = pred.pin_memory(), target.pin_memory()
+        gp = torch.full(pred.shape, float("nan")).pin_memory()
+        for zc in (1, 2, 3, 0):
+            ctx.set_zero_copy(zc)
+            gp.fill_(float("nan"))
+            t2, g2 = ctx.loss(pp, tp, batch_size=N, out_grad=gp)
+            assert g2 is gp
+            _check(t2, g2, o_terms, o_grad, ("host pinned", chunk, zc))
+            t3, g3 = ctx.loss(pp, tp, batch_size=N, want_grad=False)
+            assert g3 is None
+            _check(t3, None, o_terms, None, ("host pinned fwd", chunk, zc))
         ctx.close()
     # the module accepts CPU tensors too (reference `_device='cpu'` call shape); arithmetic still on the GPU
     mod = y.YOLOLossV1(N, S, 2, 20, _device='cpu')
     p = pred.clone().requires_grad_(True)
     mod(p, target).backward()
     _check(mod.last_terms, p.grad, o_terms, o_grad, "host module")
+
+
+def test_zero_copy_host_path_large_ragged_batch():
+    """The host-mapped kernel on a batch with a ragged tail (N*S*S % 128 != 0) against the device path."""
+    y = _y()
+    N, S = 2049, 7
+    pred, target = synth.make_loss_inputs(N, S, seed=77)
+    _, gd, td = y.yolo_loss_fused(pred.cuda(), target.cuda(), batch_size=N)
+    ctx = y.HostContext(S)
+    pp, tp = pred.pin_memory(), target.pin_memory()
+    gp = torch.empty(pred.shape).pin_memory()
+    th, gh = ctx.loss(pp, tp, batch_size=N, out_grad=gp)
+    assert torch.allclose(th, td.cpu(), rtol=2e-6, atol=0)
+    assert torch.equal(gh, gd.cpu())
+    ctx.close()
 
 
 def test_full_size_properties_config3():

@@ -41,6 +41,7 @@ SIGNATURES = {
     "yolo1_boxes_to_pixels": (_c.c_int, [_vp, _c.c_int64, _c.c_float, _c.c_float, _vp, _vp]),
     "yolo1_host_ctx_create": (_c.c_int, [_c.POINTER(_vp), _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int64]),
     "yolo1_host_ctx_destroy": (None, [_vp]),
+    "yolo1_host_ctx_set_zero_copy": (_c.c_int, [_vp, _c.c_int]),
     "yolo1_host_pin": (_c.c_int, [_vp, _c.c_size_t]),
     "yolo1_host_unpin": (_c.c_int, [_vp]),
     "yolo1_loss_fwd_bwd_host": (_c.c_int, [_vp, _vp, _vp, _vp, _vp, _c.c_int64,

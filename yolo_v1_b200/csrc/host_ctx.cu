@@ -20,6 +20,20 @@ int loss_launch_chunk(const void* pred, const int64_t ps[4], int pred_dtype, con
 
 namespace {
 constexpr int kBuf = 3;
+constexpr int kVariantHostMapped = 100;
+
+// Device-visible alias of a pinned (cudaHostAlloc / cudaHostRegister) host pointer, or nullptr for pageable
+// memory.  No allocation, no copy: a query of the driver's address map.
+template <typename T>
+T* mapped_alias(T* host) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (a.type != cudaMemoryTypeHost || a.devicePointer == nullptr) return nullptr;
+  return reinterpret_cast<T*>(a.devicePointer);
+}
 }
 
 struct yolo1_host_ctx {
@@ -34,6 +48,7 @@ struct yolo1_host_ctx {
   size_t ws_bytes;
   float* d_terms;
   float* h_terms;  // pinned
+  int zero_copy;   // 0 staged pipeline; 1 target by copy engine + pred/grad in place; 2 everything in place
 };
 
 namespace {
@@ -87,11 +102,15 @@ int yolo1_host_ctx_create(yolo1_host_ctx** out, int device, int S, int B, int C,
   YOLO1_CUDA_TRY(cudaSetDevice(device));
   yolo1_host_ctx* c = new (std::nothrow) yolo1_host_ctx();
   if (!c) return (int)cudaErrorMemoryAllocation;
+  c->zero_copy = 2;
   c->device = device, c->S = S, c->B = B, c->C = C, c->D = 5 * B + C, c->max_n = S * S * B;
   const size_t img_bytes = (size_t)S * S * c->D * 4;
   // default: ~24 MB per tensor per chunk -- long enough for PCIe to reach its plateau, short enough that the
   // pipeline fill/drain (one chunk each) is a small part of a large batch
   c->chunk = chunk_images > 0 ? chunk_images : (int64_t)((24u << 20) / img_bytes > 0 ? (24u << 20) / img_bytes : 1);
+  // chunk boundaries stay 16-byte aligned in the caller's buffers (bulk copies): an image of S*S*D floats is a
+  // multiple of 8 bytes, so an even image count per chunk is enough
+  if ((img_bytes % 16) != 0 && (c->chunk & 1)) c->chunk += 1;
   int rc = 0;
   auto fail = [&](cudaError_t e) {
     if (e != cudaSuccess && rc == 0) rc = (int)e;
@@ -124,6 +143,12 @@ void yolo1_host_ctx_destroy(yolo1_host_ctx* c) {
   free_ctx(c);
 }
 
+int yolo1_host_ctx_set_zero_copy(yolo1_host_ctx* c, int enable) {
+  if (!c) return YOLO1_ERR_ARG;
+  c->zero_copy = enable < 0 ? 0 : (enable > 3 ? 3 : enable);
+  return 0;
+}
+
 int yolo1_host_pin(void* ptr, size_t bytes) {
   if (!ptr || bytes == 0) return YOLO1_ERR_ARG;
   return (int)cudaHostRegister(ptr, bytes, cudaHostRegisterDefault);
@@ -139,11 +164,65 @@ int yolo1_loss_fwd_bwd_host(yolo1_host_ctx* c, const float* pred, const float* t
   if (!c || !pred || !target || !terms || N < 0) return YOLO1_ERR_ARG;
   if (coord_mode != YOLO1_COORD_REFERENCE && coord_mode != YOLO1_COORD_PAPER) return YOLO1_ERR_ARG;
   YOLO1_CUDA_TRY(cudaSetDevice(c->device));
-  int rc = ensure_loss_buffers(c);
-  if (rc) return rc;
   const int S = c->S, D = c->D;
   const int64_t img = (int64_t)S * S * D;
   const int64_t st[4] = {img, (int64_t)S * D, D, 1};
+  // Pinned + mapped buffers: one kernel reads the bytes it needs straight from host memory and stores the
+  // gradient straight back (loss_hostmapped_kernel) -- no staging, far fewer bytes over PCIe.
+  if ((c->zero_copy == 1 || c->zero_copy == 2) && c->B == 2 && c->C == 20 && N > 0 &&
+      N * (int64_t)S * S < 0xFFFFFFFFll) {
+    const float* dp = mapped_alias(pred);
+    const float* dt = mapped_alias(target);
+    float* dg = grad ? mapped_alias(grad) : nullptr;
+    if (dp && dt && (!grad || dg) && (uintptr_t)dp % 16 == 0 && (uintptr_t)dt % 16 == 0 && (uintptr_t)dg % 16 == 0) {
+      int rc = 0;
+      if (c->zero_copy == 1) {
+        // balanced use of the link: the copy engine streams the (dense) target chunk by chunk into HBM with
+        // large read requests, while the SMs pull only pred's confidences (one sector per cell) from host
+        // memory and bulk-store the gradient into the host buffer.  Chunks keep the `[:2]` carry (loss.cu).
+        rc = ensure_loss_buffers(c);
+        if (rc) return rc;
+        const int64_t nchunks = (N + c->chunk - 1) / c->chunk;
+        for (int64_t k = 0; k < nchunks && rc == 0; ++k) {
+          const int b = (int)(k % kBuf);
+          const int64_t n0 = k * c->chunk, n = (N - n0 < c->chunk) ? N - n0 : c->chunk;
+          YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
+          YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_tgt[b], target + n0 * img, (size_t)n * img * 4, cudaMemcpyHostToDevice,
+                                         c->s_in));
+          YOLO1_CUDA_TRY(cudaEventRecord(c->in_done[b], c->s_in));
+          YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
+          const int flags = (k == 0 ? 1 : 0) | (k == nchunks - 1 ? 2 : 0);
+          rc = yolo1::loss_launch_chunk(dp + n0 * img, st, YOLO1_DTYPE_F32, c->d_tgt[b], st, dg ? dg + n0 * img : nullptr,
+                                        st, c->d_terms, n, S, c->B, c->C, lambda_coord, lambda_noobj, inv_batch_size,
+                                        coord_mode, c->d_ws, c->ws_bytes, flags, kVariantHostMapped, c->s_k);
+          if (rc == 0) YOLO1_CUDA_TRY(cudaEventRecord(c->k_done[b], c->s_k));
+        }
+      } else {  // zero_copy == 2: everything through the SMs, one launch
+        rc = yolo1::loss_launch_chunk(dp, st, YOLO1_DTYPE_F32, dt, st, dg, st, c->d_terms, N, S, c->B, c->C,
+                                      lambda_coord, lambda_noobj, inv_batch_size, coord_mode, c->d_ws, c->ws_bytes,
+                                      3, kVariantHostMapped, c->s_k);
+      }
+      if (rc == 0) {
+        cudaError_t e = cudaMemcpyAsync(c->h_terms, c->d_terms, 5 * sizeof(float), cudaMemcpyDeviceToHost, c->s_k);
+        if (e != cudaSuccess) rc = (int)e;
+      }
+      cudaError_t e1 = cudaStreamSynchronize(c->s_k), e2 = cudaStreamSynchronize(c->s_in);
+      if (rc) return rc;
+      if (e1 != cudaSuccess) return (int)e1;
+      if (e2 != cudaSuccess) return (int)e2;
+      for (int t = 0; t < 5; ++t) terms[t] = c->h_terms[t];
+      return 0;
+    }
+  }
+  int rc = ensure_loss_buffers(c);
+  if (rc) return rc;
+  // zero_copy == 3: only pred's confidences are pulled by the SMs from the caller's (pinned, mapped) buffer; the
+  // dense target goes up and the gradient comes down through the copy engines as in the staged pipeline
+  const float* pred_alias = nullptr;
+  if (c->zero_copy == 3 && c->B == 2 && c->C == 20 && N > 0) {
+    pred_alias = mapped_alias(pred);
+    if ((uintptr_t)pred_alias % 16) pred_alias = nullptr;
+  }
   const int64_t nchunks = N == 0 ? 1 : (N + c->chunk - 1) / c->chunk;
   for (int64_t k = 0; k < nchunks; ++k) {
     const int b = (int)(k % kBuf);
@@ -152,7 +231,8 @@ int yolo1_loss_fwd_bwd_host(yolo1_host_ctx* c, const float* pred, const float* t
     // upload: the kernel that last read these staging buffers must be done
     YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
     if (bytes) {
-      YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_pred[b], pred + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
+      if (!pred_alias)
+        YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_pred[b], pred + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
       YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_tgt[b], target + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
     }
     YOLO1_CUDA_TRY(cudaEventRecord(c->in_done[b], c->s_in));
@@ -160,9 +240,10 @@ int yolo1_loss_fwd_bwd_host(yolo1_host_ctx* c, const float* pred, const float* t
     YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
     YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->out_done[b], 0));
     const int flags = (k == 0 ? 1 : 0) | (k == nchunks - 1 ? 2 : 0);
-    rc = yolo1::loss_launch_chunk(c->d_pred[b], st, YOLO1_DTYPE_F32, c->d_tgt[b], st, grad ? c->d_grad[b] : nullptr,
-                                  st, c->d_terms, n, S, c->B, c->C, lambda_coord, lambda_noobj, inv_batch_size,
-                                  coord_mode, c->d_ws, c->ws_bytes, flags, 0, c->s_k);
+    rc = yolo1::loss_launch_chunk(pred_alias ? pred_alias + n0 * img : c->d_pred[b], st, YOLO1_DTYPE_F32, c->d_tgt[b],
+                                  st, grad ? c->d_grad[b] : nullptr, st, c->d_terms, n, S, c->B, c->C, lambda_coord,
+                                  lambda_noobj, inv_batch_size, coord_mode, c->d_ws, c->ws_bytes, flags,
+                                  pred_alias ? kVariantHostMapped : 0, c->s_k);
     if (rc) break;
     YOLO1_CUDA_TRY(cudaEventRecord(c->k_done[b], c->s_k));
     // download

@@ -27,6 +27,7 @@ namespace {
 constexpr int kMaxB = 8;
 constexpr int kMaxGrid = 2048;
 constexpr int kGenericThreads = 256;
+constexpr int kVariantHostMapped = 100;  // loss_launch_chunk: the tensors are pinned, mapped host memory
 
 struct LossWs {
   unsigned long long pair;  // (~idx of 1st object cell) << 32 | (~idx of 2nd) of the current chunk; 0 = none
@@ -638,6 +639,61 @@ __global__ void __launch_bounds__(256) loss_tma_planar_kernel(const __grid_const
   block_epilogue<E, HAS_GRAD, true>(sums, m1, m2, p);
 }
 
+// ---- K1 host-resident variant: pred / target / grad are pinned, mapped HOST memory ---------------------------
+// For callers that hold host buffers (yolo1_loss_fwd_bwd_host).  Shipping the tensors to HBM first costs
+// 240 B per cell over PCIe; but a cell without object (94-98 % of them) only needs target[0] and pred[0:2].
+// Here every thread pulls exactly those two 8-byte pieces straight from host memory (one 32-byte sector
+// each over PCIe; object cells then read their full 240 B), builds the 120-byte gradient row in a shared tile
+// and the tile leaves with one bulk store directly into the caller's host gradient buffer.  One launch, no
+// staging buffers, PCIe reads and writes overlap inside the kernel.  Measured rates: tools/zc_probe.cu.
+struct GlobIn2 {
+  const float* p;
+  __device__ __forceinline__ float2 ld2(int c) const { return *reinterpret_cast<const float2*>(p + c); }
+};
+
+template <bool HAS_GRAD, int TILE>
+__global__ void __launch_bounds__(TILE) loss_hostmapped_kernel(const __grid_constant__ LossParams p) {
+  constexpr int D = 30, NOUT = 2;
+  constexpr uint32_t GB = TILE * D * sizeof(float);
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* so = reinterpret_cast<float*>(smem);
+  const int tid = threadIdx.x;
+  const int64_t full = p.cells / TILE;
+  const int64_t my_n = full > (int64_t)blockIdx.x ? (full - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const float* gp = reinterpret_cast<const float*>(p.pred);
+  float* gg = reinterpret_cast<float*>(p.grad);
+  uint64_t pol = 0;
+  if (tid == 0) pol = policy_evict_first();
+  CellSums sums = {0.f, 0.f, 0.f, 0.f};
+  uint32_t m1 = 0, m2 = 0;
+  for (int64_t k = 0; k < my_n; ++k) {
+    const int64_t tile = (int64_t)blockIdx.x + k * gridDim.x, q = tile * TILE + tid;
+    const int o = (int)(k % NOUT);
+    const GlobIn2 P{gp + q * D};
+    const GlobIn2 T{p.target + q * D};
+    const SmemOutF32 G{so + o * (TILE * D) + tid * D};
+    if (cell_b2c20<HAS_GRAD>(P, T, G, p, sums)) note_object(m1, m2, q);
+    if (HAS_GRAD) {
+      fence_async_smem();
+      if (tid == 0) bulk_wait_read<NOUT - 2>();
+      __syncthreads();
+      if (tid == 0) {
+        bulk_s2g(gg + tile * (TILE * D), so + o * (TILE * D), GB, pol);
+        bulk_commit();
+      }
+    }
+  }
+  const int64_t tail0 = full * TILE;
+  if ((int64_t)blockIdx.x == full % gridDim.x && tail0 + tid < p.cells) {
+    const int64_t q = tail0 + tid;
+    const GlobIn<float> P{gp + q * D, 1};
+    const GlobIn<float> T{p.target + q * D, 1};
+    const GlobOut<float> G{HAS_GRAD ? gg + q * D : nullptr, 1};
+    if (cell_generic<HAS_GRAD, false>(P, T, G, p, sums)) note_object(m1, m2, q);
+  }
+  block_epilogue<float, HAS_GRAD, true>(sums, m1, m2, p);
+}
+
 // ---- K1 generic kernel: any strides (e.g. the backbone's permuted NCHW view), any B, C --------------
 // One thread per cell, grid-stride.  With the channel-planar view consecutive lanes read consecutive
 // addresses of one channel plane, so every access is coalesced; channels of cells without object are
@@ -774,6 +830,23 @@ int launch_planar(const LossParams& p, int tile_imgs, cudaStream_t stream) {
   return launch_planar_n<E, HAS_GRAD, 0>(p, tile_imgs, stream);
 }
 
+template <bool HAS_GRAD>
+int launch_hostmapped(const LossParams& p, cudaStream_t stream) {
+  constexpr int TILE = 128;
+  constexpr size_t smem = 2 * TILE * 30 * sizeof(float);
+  auto kern = loss_hostmapped_kernel<HAS_GRAD, TILE>;
+  int dev = 0, sms = kNumSMs;
+  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
+  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int64_t tiles = p.cells / TILE;
+  int64_t grid = (int64_t)sms * 6;   // 31 KB and 128 threads per CTA: plenty of PCIe requests in flight
+  if (grid > tiles) grid = tiles;
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, TILE, smem, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
 template <typename E, bool HAS_GRAD>
 int launch_generic(const LossParams& p, cudaStream_t stream) {
   int dev = 0, sms = kNumSMs;
@@ -827,6 +900,10 @@ int loss_launch_chunk(const void* pred, const int64_t ps[4], int pred_dtype, con
                     (!grad || contiguous(gs, S, D)) && (uintptr_t)pred % 16 == 0 && (uintptr_t)target % 16 == 0 &&
                     (!grad || (uintptr_t)grad % 16 == 0);
   const bool bf = pred_dtype == YOLO1_DTYPE_BF16;
+  if (variant == kVariantHostMapped) {  // pointers are device-visible HOST memory (host_ctx.cu)
+    if (!fast || bf) return YOLO1_ERR_UNSUPPORTED;
+    return grad ? launch_hostmapped<true>(p, stream) : launch_hostmapped<false>(p, stream);
+  }
   if (fast) {
     if (bf) return grad ? launch_tma_variant<__nv_bfloat16, true>(p, variant, stream)
                         : launch_tma_variant<__nv_bfloat16, false>(p, variant, stream);

@@ -24,6 +24,11 @@ class HostContext:
         _lib.check(L.yolo1_host_ctx_create(ctypes.byref(self._h), self.device, self.S, self.B, self.C,
                                            int(chunk_images)), "yolo1_host_ctx_create")
 
+    def set_zero_copy(self, enable):
+        """Pinned+mapped loss buffers: 2 (default) = read / written in place by one kernel; 1 = target streamed by
+        the copy engine, pred / grad in place; 3 = only pred in place; 0 = staged H2D / kernel / D2H pipeline."""
+        _lib.check(_lib.lib().yolo1_host_ctx_set_zero_copy(self._h, int(enable)), "yolo1_host_ctx_set_zero_copy")
+
     def close(self):
         if self._h:
             _lib.lib().yolo1_host_ctx_destroy(self._h)
