@@ -91,6 +91,21 @@ YOLO1_API int yolo1_loss_fwd_bwd_ex(const void* pred, const int64_t pred_strides
                           void* workspace, size_t workspace_bytes, int variant, void* stream);
 
 /*
+ * Loss with the head's epilogue fused in (backbones/OriginResNet.py:186-188, OriginDenseNet.py:124-128: the
+ * network ends in `torch.sigmoid` followed by `permute(0,2,3,1)`): `logits` are the PRE-sigmoid outputs seen
+ * through the same [N,S,S,D] strides (the permuted NCHW view is read in place); the kernel applies the sigmoid
+ * on load and returns d total / d logit = d total / d p * p (1 - p) -- one full read + write of the S x S x D
+ * tensor less in the forward and in the backward pass, and no sigmoid kernels.  Same terms as
+ * yolo1_loss_fwd_bwd(sigmoid(logits), ...).
+ */
+YOLO1_API int yolo1_loss_fwd_bwd_logits(const void* logits, const int64_t logit_strides[4], int dtype,
+                                        const float* target, const int64_t target_strides[4],
+                                        void* grad, const int64_t grad_strides[4], float* terms,
+                                        int64_t N, int S, int B, int C,
+                                        float lambda_coord, float lambda_noobj, float inv_batch_size, int coord_mode,
+                                        void* workspace, size_t workspace_bytes, void* stream);
+
+/*
  * grad *= *grad_out_dev, in place, for autograd's backward(grad_output) (train.py:171 calls
  * loss.backward() with grad_output = 1; AMP loss scaling makes it != 1).  The kernel reads the scalar
  * on the device and returns without touching memory when it is exactly 1.0f, so the usual training
@@ -146,6 +161,19 @@ YOLO1_API int yolo1_decode_nms(const void* pred, const int64_t pred_strides[4], 
  */
 YOLO1_API int yolo1_boxes_to_pixels(const float* boxes, int64_t n_boxes, float img_w, float img_h, int32_t* pixels,
                                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Target encoder: replaces yoloDataset.encoder (utils/YOLODataLoader.py:200-230), batched.
+ * boxes [n_obj,4] = (cx, cy, w, h) normalised to the image, labels [n_obj], offsets [N+1] (CSR: image n owns
+ * objects offsets[n] .. offsets[n+1]-1, in the order the reference would iterate them) -- all device memory.
+ * target [N,S,S,5B+C] float32 contiguous is fully written (zeros where no object): cell = ceil(c / fl32(1/S)) - 1,
+ * the last object that falls into a cell wins, every confidence slot 1, class one-hot, the same
+ * (dx, dy, w, h) in every box slot.  Bit-exact with the reference's fp32 arithmetic.
+ * status: device int32, set to 1 if a centre or label was outside the grid / class range (the reference
+ * raises IndexError there; such objects are skipped), else 0.  One image must fit 96 KB.
+ * ---------------------------------------------------------------------------------------------- */
+YOLO1_API int yolo1_encode_targets(const float* boxes, const int32_t* labels, const int64_t* offsets, int64_t N,
+                                   int S, int B, int C, float* target, int32_t* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points: the same path for callers that hold HOST memory (the reference's callers

@@ -268,6 +268,57 @@ def gen_map(meta):
     meta["map_case"] = dict(S=S, mAP=m, aps=aps, gt=[[k[0], k[1], v] for k, v in sorted(gt.items())])
 
 
+def load_reference_encoder():
+    """The reference's target encoder is a method of its dataset class (utils/YOLODataLoader.py:200-230); the module
+    imports imgaug (absent here) at the top, so stub that import -- the encoder itself only uses torch."""
+    import importlib.util
+    import types
+    for name in ("imgaug", "imgaug.augmenters"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["imgaug"].seed = lambda *a, **k: None
+    sys.modules["imgaug"].augmenters = sys.modules["imgaug.augmenters"]
+    spec = importlib.util.spec_from_file_location("ref_yolo_dataloader", "/root/reference/utils/YOLODataLoader.py")
+    mod = importlib.util.module_from_spec(spec)
+    sys.dont_write_bytecode = True
+    spec.loader.exec_module(mod)
+    return mod.yoloDataset
+
+
+def gen_encoder(meta):
+    DS = load_reference_encoder()
+    out = {}
+    rng = np.random.RandomState(17)
+    for name, S, n_img in [("enc_s7", 7, 64), ("enc_s14", 14, 32), ("enc_s3_b1", 3, 8)]:
+        B, C = (1, 5) if name.endswith("b1") else (2, 20)
+        ds = object.__new__(DS)
+        ds.S, ds.B, ds.C = S, B, C
+        boxes, labels, offsets, targets = [], [], [0], []
+        for n in range(n_img):
+            k = 0 if n % 9 == 0 else rng.randint(1, 7)          # empty images too (:209-210)
+            bx = rng.rand(k, 4).astype(np.float32)
+            if k and n % 5 == 0:
+                bx[0, :2] = [1.0, 1.0]                           # right / bottom edge
+            if k and n % 7 == 0:
+                bx[-1, :2] = [0.0, 0.25]                         # ij = -1 wraps to the last column (Python indexing)
+            if k > 1 and n % 3 == 0:
+                bx[1, :2] = bx[0, :2]                            # two objects in one cell: the last one wins
+            if k and n % 4 == 0:
+                bx[0, 0] = np.float32(3.0 / S)                   # exactly on a cell boundary
+            lb = rng.randint(0, C, size=k)
+            t = ds.encoder(torch.from_numpy(bx).reshape(-1, 4), torch.from_numpy(lb))
+            boxes.append(bx.reshape(-1, 4)); labels.append(lb); offsets.append(offsets[-1] + k); targets.append(t.numpy())
+        boxes = np.concatenate(boxes, 0).astype(np.float32)
+        labels = np.concatenate(labels, 0).astype(np.int32)
+        target = np.stack(targets).astype(np.float32)
+        mine = O.encode(boxes, labels, offsets, S, B, C)
+        assert np.array_equal(mine.view(np.uint32), target.view(np.uint32)), name
+        out[name + "/boxes"], out[name + "/labels"] = boxes, labels
+        out[name + "/offsets"], out[name + "/target"] = np.asarray(offsets, np.int64), target
+        out[name + "/params"] = np.array([S, B, C], np.int64)
+        print("encoder set %-10s images=%d objects=%d  bit-exact vs C oracle" % (name, n_img, len(labels)))
+    np.savez_compressed(os.path.join(GOLD, "encoder_cases.npz"), **out)
+
+
 def time_reference(meta):
     """Timing of the reference's own Python path in THIS container (context for DESIGN.md/BASELINE.md)."""
     torch.set_num_threads(os.cpu_count())
@@ -297,6 +348,7 @@ def main():
     gen_decode(meta)
     gen_misc(meta)
     gen_map(meta)
+    gen_encoder(meta)
     time_reference(meta)
     with open(os.path.join(GOLD, "golden_meta.json"), "w") as f:
         json.dump(meta, f, indent=1)

@@ -390,6 +390,61 @@ int yolo1_oracle_decode_nms(const float* pred, const int64_t st[4], int64_t N, i
   return 0;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* encoder : utils/YOLODataLoader.py:200-230.  Bit-exact fp32, every operation rounds separately. */
+/* ------------------------------------------------------------------------------------------ */
+
+/*
+ * One image.  boxes [n,4] = (cx, cy, w, h) normalised to the image, labels [n]; target [S,S,5B+C]
+ * contiguous, fully written (zero where no object).  In input order, for every object:
+ *   :218-219 ij = ceil(cxcy / cell_size) - 1   (cell_size = fl32(1/S); fp32 division)
+ *   :220     the cell is reset to zero, so the LAST object that falls into a cell wins
+ *   :221-222 every confidence slot = 1, class one-hot
+ *   :223-224 delta_xy = (cxcy - ij*cell_size) / cell_size
+ *   :225-227 the same (delta_x, delta_y, w, h) in every box slot
+ * Python indexing: ij = -1 (cx or cy == 0) addresses the last row / column.  Returns 0, or -2 when an
+ * index falls outside [-S, S) (the reference raises IndexError there); the target is then unspecified.
+ */
+int yolo1_oracle_encode_image(const float* boxes, const int32_t* labels, int n, int S, int B, int C,
+                              float* target) {
+  const int D = 5 * B + C;
+  const float cs = (float)(1.0 / (double)S);
+  memset(target, 0, sizeof(float) * (size_t)S * S * D);
+  for (int k = 0; k < n; ++k) {
+    const float cx = boxes[4 * k], cy = boxes[4 * k + 1], w = boxes[4 * k + 2], h = boxes[4 * k + 3];
+    const float fi = ceilf(cx / cs) - 1.0f, fj = ceilf(cy / cs) - 1.0f;
+    int col = (int)fi, row = (int)fj;
+    if (col < -S || col >= S || row < -S || row >= S) return -2;
+    if (labels[k] < -C || labels[k] >= C) return -2;
+    if (col < 0) col += S;
+    if (row < 0) row += S;
+    float* t = target + ((size_t)row * S + col) * D;
+    for (int c = 0; c < D; ++c) t[c] = 0.0f;
+    for (int b = 0; b < B; ++b) t[b] = 1.0f;
+    t[5 * B + (labels[k] < 0 ? labels[k] + C : labels[k])] = 1.0f;
+    const float dx = (cx - fi * cs) / cs, dy = (cy - fj * cs) / cs;
+    for (int b = 0; b < B; ++b) {
+      t[B + 4 * b] = dx;
+      t[B + 4 * b + 1] = dy;
+      t[B + 4 * b + 2] = w;
+      t[B + 4 * b + 3] = h;
+    }
+  }
+  return 0;
+}
+
+/* batched: offsets [N+1] into boxes/labels (CSR); target [N,S,S,5B+C] */
+int yolo1_oracle_encode(const float* boxes, const int32_t* labels, const int64_t* offsets, int64_t N, int S,
+                        int B, int C, float* target) {
+  const size_t img = (size_t)S * S * (5 * B + C);
+  for (int64_t n = 0; n < N; ++n) {
+    int rc = yolo1_oracle_encode_image(boxes + 4 * offsets[n], labels + offsets[n],
+                                       (int)(offsets[n + 1] - offsets[n]), S, B, C, target + n * img);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 int yolo1_oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

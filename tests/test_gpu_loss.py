@@ -187,6 +187,41 @@ def test_module_matches_reference_call_shape_and_autograd():
     assert abs(float(l2) - float(o_terms[4])) <= TOL * abs(float(o_terms[4]))
 
 
+@pytest.mark.parametrize("layout", ["nhwc", "planar", "strided"])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_fused_sigmoid_head(layout, dtype):
+    """from_logits: the head's sigmoid (OriginResNet.py:188) and its backward inside the loss kernel.  Same terms
+    as the un-fused call on sigmoid(z); gradient = d loss / d p * p (1 - p)."""
+    y = _y()
+    N, S = 37, 7
+    _, target = synth.make_loss_inputs(N, S, seed=5, p_obj=0.2, variant="mixed")
+    z = torch.randn(N, S, S, 30, generator=torch.Generator().manual_seed(1)) * 1.5
+    if dtype == "bf16":
+        z = z.to(torch.bfloat16)
+    zd = z.double()
+    p64 = torch.sigmoid(zd)
+    o_terms, o_grad = O.loss(p64.float().numpy(), target.numpy(), batch_size=N)
+    want = o_grad.astype(np.float64) * (p64 * (1 - p64)).numpy()
+    zc = z.cuda()
+    if layout == "planar":
+        zc = zc.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+    elif layout == "strided":
+        zc = torch.zeros(N, S, S, 32, dtype=z.dtype, device="cuda")[..., :30].copy_(z)
+    _, grad, terms = y.yolo_loss_fused(zc, target.cuda(), batch_size=N, from_logits=True)
+    assert grad.stride() == zc.stride() or layout == "strided"
+    tol = 2e-5 if dtype == "f32" else 2.0 ** -7
+    t = terms.cpu().numpy()
+    assert np.all(np.abs(t - o_terms) <= 2e-5 * np.abs(o_terms) + 1e-7)
+    g = grad.float().cpu().numpy()
+    assert np.abs(g - want).max() <= tol * np.abs(want).max()
+    # module form, through autograd, with the pre-sigmoid tensor as the leaf
+    if dtype == "f32":
+        mod = y.YOLOLossV1(N, S, 2, 20, from_logits=True)
+        leaf = zc.clone().requires_grad_(True)
+        mod(leaf, target.cuda()).backward()
+        assert torch.equal(leaf.grad, grad)
+
+
 def test_module_logging_hooks():
     y = _y()
     pred, target = synth.make_loss_inputs(4, 7, seed=1, p_obj=0.2)

@@ -9,6 +9,7 @@ from .loss import YOLOLossV1, yolo_loss_fused, scale_grad_          # noqa: F401
 from .decode import (decoder, nms, decode_nms_batched, decode_batched, nms_batched,   # noqa: F401
                      compute_iou_matrix, convert_CxCyWH_to_X1Y1X2Y2)
 from .voc import voc_eval, voc_ap, run_test_mAP, detections_to_voc_preds, boxes_to_pixels, VOC_CLASSES  # noqa: F401
+from .encode import encode_targets, encoder, pack_objects             # noqa: F401
 from .host import HostContext                                        # noqa: F401
 from .dist import shard_range, all_reduce_terms, sharded_loss        # noqa: F401
 

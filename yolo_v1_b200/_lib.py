@@ -31,6 +31,10 @@ SIGNATURES = {
                                          _c.c_int64, _c.c_int, _c.c_int, _c.c_int,
                                          _c.c_float, _c.c_float, _c.c_float, _c.c_int,
                                          _vp, _c.c_size_t, _c.c_int, _vp]),
+    "yolo1_loss_fwd_bwd_logits": (_c.c_int, [_vp, _i64p, _c.c_int, _vp, _i64p, _vp, _i64p, _vp,
+                                             _c.c_int64, _c.c_int, _c.c_int, _c.c_int,
+                                             _c.c_float, _c.c_float, _c.c_float, _c.c_int,
+                                             _vp, _c.c_size_t, _vp]),
     "yolo1_scale_grad": (_c.c_int, [_vp, _c.c_int, _c.c_int64, _vp, _vp]),
     "yolo1_decode": (_c.c_int, [_vp, _i64p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int,
                                 _c.c_double, _vp, _vp, _vp, _vp, _vp]),
@@ -39,6 +43,7 @@ SIGNATURES = {
     "yolo1_decode_nms": (_c.c_int, [_vp, _i64p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int,
                                     _c.c_double, _c.c_float, _c.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "yolo1_boxes_to_pixels": (_c.c_int, [_vp, _c.c_int64, _c.c_float, _c.c_float, _vp, _vp]),
+    "yolo1_encode_targets": (_c.c_int, [_vp, _vp, _vp, _c.c_int64, _c.c_int, _c.c_int, _c.c_int, _vp, _vp, _vp]),
     "yolo1_host_ctx_create": (_c.c_int, [_c.POINTER(_vp), _c.c_int, _c.c_int, _c.c_int, _c.c_int, _c.c_int64]),
     "yolo1_host_ctx_destroy": (None, [_vp]),
     "yolo1_host_ctx_set_zero_copy": (_c.c_int, [_vp, _c.c_int]),

@@ -1,0 +1,117 @@
+// encode.cu -- target encoder on the GPU.
+//
+// Replaces yoloDataset.encoder (reference utils/YOLODataLoader.py:200-230) for a whole batch: ragged lists of
+// (cx, cy, w, h) boxes and labels (CSR offsets) -> the dense target tensor [N,S,S,5B+C] the loss consumes.
+// The reference builds a 94-98 % zero tensor on the host and ships it over PCIe; here only the object lists
+// cross (a few dozen bytes per image) and the tensor is produced at HBM write speed.  Built with -fmad=false:
+// the cell index and the in-cell offsets are bit-exact with the reference's fp32 arithmetic.
+//
+// A CTA owns a group of G whole images: the tile is zeroed in shared memory, thread i scatters image i's objects
+// in input order (the reference resets the cell before writing, so the LAST object in a cell wins), and the
+// finished tile leaves with one bulk store (cp.async.bulk, SASS UBLKCP) -- a write-only stream of 120 B per cell.
+#include "common.cuh"
+
+namespace yolo1 {
+namespace {
+
+struct EncodeParams {
+  const float* boxes;
+  const int32_t* labels;
+  const int64_t* offsets;
+  float* target;
+  int32_t* status;  // device int: set to 1 when a centre or label falls outside the grid / class range
+  int64_t N;
+  int S, B, C, G;
+  float cs;  // fl32(1/S)
+};
+
+__global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ EncodeParams p) {
+  extern __shared__ __align__(128) unsigned char raw[];
+  float* tile = reinterpret_cast<float*>(raw);
+  const int S = p.S, B = p.B, C = p.C, D = 5 * B + C;
+  const int img = S * S * D;
+  uint64_t pol = 0;
+  if (threadIdx.x == 0) pol = policy_evict_first();
+  for (int64_t g0 = (int64_t)blockIdx.x * p.G; g0 < p.N; g0 += (int64_t)gridDim.x * p.G) {
+    const int n_img = (int)((p.N - g0 < p.G) ? p.N - g0 : p.G);
+    const int total = n_img * img;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) tile[t] = 0.f;
+    __syncthreads();
+    if ((int)threadIdx.x < n_img) {
+      float* timg = tile + threadIdx.x * img;
+      const int64_t k0 = p.offsets[g0 + threadIdx.x], k1 = p.offsets[g0 + threadIdx.x + 1];
+      for (int64_t k = k0; k < k1; ++k) {
+        const float cx = p.boxes[4 * k], cy = p.boxes[4 * k + 1], w = p.boxes[4 * k + 2], h = p.boxes[4 * k + 3];
+        const float fi = ceilf(__fdiv_rn(cx, p.cs)) - 1.0f, fj = ceilf(__fdiv_rn(cy, p.cs)) - 1.0f;  // :218-219
+        int col = (int)fi, row = (int)fj, lab = p.labels[k];
+        if (col < -S || col >= S || row < -S || row >= S || lab < -C || lab >= C) {  // reference: IndexError
+          atomicExch(p.status, 1);
+          continue;
+        }
+        if (col < 0) col += S;  // Python indexing: -1 is the last row / column
+        if (row < 0) row += S;
+        if (lab < 0) lab += C;
+        float* t = timg + (row * S + col) * D;
+        for (int c = 0; c < D; ++c) t[c] = 0.f;  // :220 reset -> the last object in a cell wins
+        const float dx = __fdiv_rn(cx - fi * p.cs, p.cs), dy = __fdiv_rn(cy - fj * p.cs, p.cs);  // :223-224
+        for (int b = 0; b < B; ++b) {
+          t[b] = 1.f;  // :221
+          t[B + 4 * b] = dx, t[B + 4 * b + 1] = dy, t[B + 4 * b + 2] = w, t[B + 4 * b + 3] = h;  // :225-227
+        }
+        t[5 * B + lab] = 1.f;  // :222
+      }
+    }
+    float* dst = p.target + g0 * img;
+    const bool bulk = (((size_t)total * 4) % 16 == 0) && ((uintptr_t)dst % 16 == 0);
+    if (bulk) {
+      fence_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        bulk_s2g(dst, tile, (uint32_t)total * 4u, pol);
+        bulk_commit();
+        bulk_wait_read<0>();  // the tile is zeroed again right after
+      }
+      __syncthreads();
+    } else {
+      __syncthreads();
+      for (int t = threadIdx.x; t < total; t += blockDim.x) dst[t] = tile[t];
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_all<0>();
+}
+
+}  // namespace
+}  // namespace yolo1
+
+extern "C" YOLO1_API int yolo1_encode_targets(const float* boxes, const int32_t* labels, const int64_t* offsets, int64_t N, int S,
+                                    int B, int C, float* target, int32_t* status, void* stream) {
+  using namespace yolo1;
+  if (N < 0 || S <= 0 || B <= 0 || C <= 0) return YOLO1_ERR_ARG;
+  if (N == 0) return 0;
+  if (!offsets || !target || !status) return YOLO1_ERR_ARG;  // boxes / labels may be null when there is no object
+  if (5 * B + C > 128 || (int64_t)S * S * (5 * B + C) * 4 > 96 * 1024) return YOLO1_ERR_UNSUPPORTED;
+  if ((uintptr_t)boxes % 4 || (uintptr_t)labels % 4 || (uintptr_t)offsets % 8 || (uintptr_t)target % 4 ||
+      (uintptr_t)status % 4)
+    return YOLO1_ERR_ALIGN;
+  EncodeParams p;
+  p.boxes = boxes, p.labels = labels, p.offsets = offsets, p.target = target, p.status = status;
+  p.N = N, p.S = S, p.B = B, p.C = C;
+  p.cs = (float)(1.0 / (double)S);
+  const size_t img_bytes = (size_t)S * S * (5 * B + C) * 4;
+  int G = (int)((48 * 1024) / img_bytes);  // ~48 KB tiles: 4 CTAs per SM keep the store queue busy
+  if (G < 1) G = 1;
+  if (G > 256) G = 256;
+  if (G > 1 && (G & 1)) G -= 1;  // an even image count keeps every tile a multiple of 16 bytes
+  p.G = G;
+  const size_t smem = (size_t)G * img_bytes;
+  YOLO1_CUDA_TRY(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = kNumSMs;
+  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
+  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int64_t grid = (N + G - 1) / G;
+  if (grid > (int64_t)sms * 4) grid = (int64_t)sms * 4;
+  YOLO1_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int32_t), (cudaStream_t)stream));
+  encode_kernel<<<(unsigned)grid, 256, smem, (cudaStream_t)stream>>>(p);
+  return (int)cudaGetLastError();
+}

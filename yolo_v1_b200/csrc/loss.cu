@@ -51,6 +51,7 @@ struct LossParams {
   float k2;    // 2 / batch_size
   int coord_mode;
   int last_chunk;
+  int logits;  // 1: `pred` holds the head's pre-sigmoid outputs; the kernel applies sigmoid and returns d loss / d logit
 };
 
 struct CellSums {
@@ -161,17 +162,56 @@ struct SmemOut<__nv_bfloat16> {
   using type = SmemOutBF16;
 };
 
+// head epilogue fusion (backbones/OriginResNet.py:186-188: ... bn_end -> torch.sigmoid -> permute): p = sigmoid(z),
+// d loss / d z = d loss / d p * p (1 - p)
+__device__ __forceinline__ float sigmoid_(float z) { return 1.0f / (1.0f + expf(-z)); }
+__device__ __forceinline__ float dsigmoid_(float z) {
+  const float pz = sigmoid_(z);
+  return pz * (1.0f - pz);
+}
+
 template <typename E>
 struct GlobIn {
   const E* p;
   int64_t cs;
-  __device__ __forceinline__ float ld(int c) const { return ld_elem(p + c * cs); }
+  bool sig;  // values are logits: apply sigmoid on load
+  __device__ __forceinline__ float ld(int c) const {
+    const float v = ld_elem(p + c * cs);
+    return sig ? sigmoid_(v) : v;
+  }
 };
 template <typename E>
 struct GlobOut {
   E* p;
   int64_t cs;
-  __device__ __forceinline__ void st(int c, float v) const { st_elem(p + c * cs, v); }
+  const E* z;  // logits of the same cell (sig only)
+  int64_t zs;
+  bool sig;
+  __device__ __forceinline__ void st(int c, float v) const {
+    if (sig && v != 0.f) v *= dsigmoid_(ld_elem(z + c * zs));
+    st_elem(p + c * cs, v);
+  }
+};
+// wrappers that put the sigmoid head in front of any pair accessor (shared-memory tiles)
+template <typename In>
+struct SigIn {
+  In in;
+  __device__ __forceinline__ float2 ld2(int c) const {
+    const float2 v = in.ld2(c);
+    return make_float2(sigmoid_(v.x), sigmoid_(v.y));
+  }
+};
+template <typename Out, typename In>
+struct SigOut {
+  Out out;
+  In z;  // the logits of the same cell; read before the (possibly aliasing) store
+  __device__ __forceinline__ void st2(int c, float x, float y) const {
+    if (x != 0.f || y != 0.f) {
+      const float2 v = z.ld2(c);
+      x *= dsigmoid_(v.x), y *= dsigmoid_(v.y);
+    }
+    out.st2(c, x, y);
+  }
 };
 
 // channel-planar tile in shared memory: channel c of a cell lives `plane` elements apart (lanes <-> consecutive
@@ -444,9 +484,11 @@ __device__ __noinline__ void block_epilogue(CellSums s, uint32_t m1, uint32_t m2
         if (seen < 2 && p.coord_mode == YOLO1_COORD_REFERENCE) {
           // v1Loss.py:101 `[:2]`: this object is one of the first two of the call -> plain form
           const int64_t q = (int64_t)(0xFFFFFFFFu - c[t]);
-          GlobIn<E> P{reinterpret_cast<const E*>(p.pred) + cell_offset<E>(p.ps, q, p.S), p.ps[3]};
-          GlobIn<float> T{p.target + cell_offset<float>(p.ts, q, p.S), p.ts[3]};
-          GlobOut<E> G{HAS_GRAD ? reinterpret_cast<E*>(p.grad) + cell_offset<E>(p.gs, q, p.S) : nullptr, p.gs[3]};
+          const E* zq = reinterpret_cast<const E*>(p.pred) + cell_offset<E>(p.ps, q, p.S);
+          GlobIn<E> P{zq, p.ps[3], p.logits != 0};
+          GlobIn<float> T{p.target + cell_offset<float>(p.ts, q, p.S), p.ts[3], false};
+          GlobOut<E> G{HAS_GRAD ? reinterpret_cast<E*>(p.grad) + cell_offset<E>(p.gs, q, p.S) : nullptr, p.gs[3], zq,
+                       p.ps[3], p.logits != 0};
           CellSums d = {0.f, 0.f, 0.f, 0.f};
           cell_generic<HAS_GRAD, true>(P, T, G, p, d);
           t4[0] += (double)d.loc;
@@ -476,7 +518,7 @@ __device__ __noinline__ void block_epilogue(CellSums s, uint32_t m1, uint32_t m2
 }
 
 // ---- K1 fast kernel: contiguous layout, TMA in / TMA out ----------------------------------------------
-template <typename E, bool HAS_GRAD, int TILE, int STAGES, int NOUT>
+template <typename E, bool HAS_GRAD, int TILE, int STAGES, int NOUT, bool SIG = false>
 __global__ void __launch_bounds__(TILE) loss_tma_kernel(const __grid_constant__ LossParams p) {
   constexpr int D = 30;
   constexpr uint32_t PB = TILE * D * sizeof(E), TB = TILE * D * sizeof(float), GB = PB;
@@ -524,8 +566,12 @@ __global__ void __launch_bounds__(TILE) loss_tma_kernel(const __grid_constant__ 
     // in-place: every thread reads its own cell's 30 values before it overwrites them with the gradient
     E* gtile = INPLACE ? sp + s * (TILE * D) : so + o * (TILE * D);
     const GOut G{gtile + tid * D};
-    if (cell_b2c20<HAS_GRAD>(P, T, G, p, sums))
-      note_object(m1, m2, ((int64_t)blockIdx.x + k * gridDim.x) * TILE + tid);
+    bool obj;
+    if (SIG)
+      obj = cell_b2c20<HAS_GRAD>(SigIn<PIn>{P}, T, SigOut<GOut, PIn>{G, P}, p, sums);
+    else
+      obj = cell_b2c20<HAS_GRAD>(P, T, G, p, sums);
+    if (obj) note_object(m1, m2, ((int64_t)blockIdx.x + k * gridDim.x) * TILE + tid);
     if (HAS_GRAD) {
       fence_async_smem();  // my shared-memory gradient writes -> visible to the copy engine
       if (!INPLACE && tid == 0) bulk_wait_read<(NOUT >= 2 ? NOUT - 2 : 0)>();  // buffer (k+1) % NOUT is free again
@@ -546,9 +592,9 @@ __global__ void __launch_bounds__(TILE) loss_tma_kernel(const __grid_constant__ 
   const int64_t tail0 = full * TILE;
   if ((int64_t)blockIdx.x == full % gridDim.x && tail0 + tid < p.cells) {
     const int64_t q = tail0 + tid;
-    const GlobIn<E> P{gp + q * D, 1};
-    const GlobIn<float> T{p.target + q * D, 1};
-    const GlobOut<E> G{HAS_GRAD ? gg + q * D : nullptr, 1};
+    const GlobIn<E> P{gp + q * D, 1, SIG};
+    const GlobIn<float> T{p.target + q * D, 1, false};
+    const GlobOut<E> G{HAS_GRAD ? gg + q * D : nullptr, 1, gp + q * D, 1, SIG};
     if (cell_generic<HAS_GRAD, false>(P, T, G, p, sums)) note_object(m1, m2, q);
   }
   block_epilogue<E, HAS_GRAD, true>(sums, m1, m2, p);
@@ -559,7 +605,7 @@ __global__ void __launch_bounds__(TILE) loss_tma_kernel(const __grid_constant__ 
 // An image's 30 planes are one contiguous block, so a tile of `tile_imgs` whole images still moves with one
 // bulk copy per tensor; one thread per cell reads its channels S*S elements apart (conflict-free) and writes
 // the gradient tile in the same planar layout, so `permute`'s backward stays a free view.
-template <typename E, bool HAS_GRAD, int STAGES, int NOUT>
+template <typename E, bool HAS_GRAD, int STAGES, int NOUT, bool SIG = false>
 __global__ void __launch_bounds__(256) loss_tma_planar_kernel(const __grid_constant__ LossParams p, int tile_imgs) {
   constexpr int D = 30;
   const int SS = p.S * p.S, tile_cells = tile_imgs * SS, tile_elems = tile_cells * D;
@@ -608,8 +654,12 @@ __global__ void __launch_bounds__(256) loss_tma_planar_kernel(const __grid_const
       const PlanarIn<E> P{sp + s * tile_elems + poff, SS};
       const SmemInF32 T{st + s * tile_elems + tid * D};
       const PlanarOut<E> G{gtile + poff, SS};
-      if (cell_b2c20<HAS_GRAD>(P, T, G, p, sums))
-        note_object(m1, m2, ((int64_t)blockIdx.x + k * gridDim.x) * tile_cells + tid);
+      bool obj;
+      if (SIG)
+        obj = cell_b2c20<HAS_GRAD>(SigIn<PlanarIn<E>>{P}, T, SigOut<PlanarOut<E>, PlanarIn<E>>{G, P}, p, sums);
+      else
+        obj = cell_b2c20<HAS_GRAD>(P, T, G, p, sums);
+      if (obj) note_object(m1, m2, ((int64_t)blockIdx.x + k * gridDim.x) * tile_cells + tid);
     }
     if (HAS_GRAD) {
       fence_async_smem();
@@ -631,9 +681,10 @@ __global__ void __launch_bounds__(256) loss_tma_planar_kernel(const __grid_const
   const int64_t tail0 = full * tile_cells;
   if ((int64_t)blockIdx.x == full % gridDim.x && tail0 + tid < p.cells && tid < tile_cells) {
     const int64_t q = tail0 + tid;
-    const GlobIn<E> P{gp + cell_offset<E>(p.ps, q, p.S), p.ps[3]};
-    const GlobIn<float> T{p.target + cell_offset<float>(p.ts, q, p.S), p.ts[3]};
-    const GlobOut<E> G{HAS_GRAD ? gg + cell_offset<E>(p.gs, q, p.S) : nullptr, p.gs[3]};
+    const E* zq = gp + cell_offset<E>(p.ps, q, p.S);
+    const GlobIn<E> P{zq, p.ps[3], SIG};
+    const GlobIn<float> T{p.target + cell_offset<float>(p.ts, q, p.S), p.ts[3], false};
+    const GlobOut<E> G{HAS_GRAD ? gg + cell_offset<E>(p.gs, q, p.S) : nullptr, p.gs[3], zq, p.ps[3], SIG};
     if (cell_generic<HAS_GRAD, false>(P, T, G, p, sums)) note_object(m1, m2, q);
   }
   block_epilogue<E, HAS_GRAD, true>(sums, m1, m2, p);
@@ -686,9 +737,9 @@ __global__ void __launch_bounds__(TILE) loss_hostmapped_kernel(const __grid_cons
   const int64_t tail0 = full * TILE;
   if ((int64_t)blockIdx.x == full % gridDim.x && tail0 + tid < p.cells) {
     const int64_t q = tail0 + tid;
-    const GlobIn<float> P{gp + q * D, 1};
-    const GlobIn<float> T{p.target + q * D, 1};
-    const GlobOut<float> G{HAS_GRAD ? gg + q * D : nullptr, 1};
+    const GlobIn<float> P{gp + q * D, 1, false};
+    const GlobIn<float> T{p.target + q * D, 1, false};
+    const GlobOut<float> G{HAS_GRAD ? gg + q * D : nullptr, 1, nullptr, 0, false};
     if (cell_generic<HAS_GRAD, false>(P, T, G, p, sums)) note_object(m1, m2, q);
   }
   block_epilogue<float, HAS_GRAD, true>(sums, m1, m2, p);
@@ -704,9 +755,11 @@ __global__ void __launch_bounds__(kGenericThreads) loss_generic_kernel(const __g
   uint32_t m1 = 0, m2 = 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < p.cells; q += stride) {
-    const GlobIn<E> P{reinterpret_cast<const E*>(p.pred) + cell_offset<E>(p.ps, q, p.S), p.ps[3]};
-    const GlobIn<float> T{p.target + cell_offset<float>(p.ts, q, p.S), p.ts[3]};
-    const GlobOut<E> G{HAS_GRAD ? reinterpret_cast<E*>(p.grad) + cell_offset<E>(p.gs, q, p.S) : nullptr, p.gs[3]};
+    const E* zq = reinterpret_cast<const E*>(p.pred) + cell_offset<E>(p.ps, q, p.S);
+    const GlobIn<E> P{zq, p.ps[3], p.logits != 0};
+    const GlobIn<float> T{p.target + cell_offset<float>(p.ts, q, p.S), p.ts[3], false};
+    const GlobOut<E> G{HAS_GRAD ? reinterpret_cast<E*>(p.grad) + cell_offset<E>(p.gs, q, p.S) : nullptr, p.gs[3], zq,
+                       p.ps[3], p.logits != 0};
     if (cell_generic<HAS_GRAD, false>(P, T, G, p, sums)) note_object(m1, m2, q);
   }
   block_epilogue<E, HAS_GRAD, false>(sums, m1, m2, p);  // no bulk stores in flight here
@@ -737,11 +790,11 @@ bool contiguous(const int64_t st[4], int S, int D) {
   return st[3] == 1 && st[2] == D && st[1] == (int64_t)S * D && st[0] == (int64_t)S * S * D;
 }
 
-template <typename E, bool HAS_GRAD, int TILE, int STAGES, int NOUT>
+template <typename E, bool HAS_GRAD, int TILE, int STAGES, int NOUT, bool SIG = false>
 int launch_tma(const LossParams& p, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * TILE * 30 * (sizeof(E) + 4) + (size_t)NOUT * TILE * 30 * sizeof(E) +
                           STAGES * sizeof(uint64_t);
-  auto kern = loss_tma_kernel<E, HAS_GRAD, TILE, STAGES, NOUT>;
+  auto kern = loss_tma_kernel<E, HAS_GRAD, TILE, STAGES, NOUT, SIG>;
   YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = kNumSMs, per_sm = 1;
   YOLO1_CUDA_TRY(cudaGetDevice(&dev));
@@ -759,6 +812,7 @@ int launch_tma(const LossParams& p, cudaStream_t stream) {
 
 template <typename E, bool HAS_GRAD>
 int launch_tma_variant(const LossParams& p, int variant, cudaStream_t stream) {
+  if (p.logits) return launch_tma<E, HAS_GRAD, 128, 2, 2, true>(p, stream);  // one launch shape with the fused head
   switch (variant) {
     case 0:
     case 1: return launch_tma<E, HAS_GRAD, 128, 2, 2>(p, stream);
@@ -797,14 +851,14 @@ int planar_tile_imgs(int S, size_t esz, int target_cells) {
   return t;
 }
 
-template <typename E, bool HAS_GRAD, int NOUT>
+template <typename E, bool HAS_GRAD, int NOUT, bool SIG>
 int launch_planar_n(const LossParams& p, int tile_imgs, cudaStream_t stream) {
   constexpr int STAGES = 2;
   const int tile_cells = tile_imgs * p.S * p.S;
   const size_t smem = (size_t)STAGES * tile_cells * 30 * (sizeof(E) + 4) + (size_t)NOUT * tile_cells * 30 * sizeof(E) +
                       STAGES * sizeof(uint64_t);
   const int threads = (tile_cells + 31) / 32 * 32;
-  auto kern = loss_tma_planar_kernel<E, HAS_GRAD, STAGES, NOUT>;
+  auto kern = loss_tma_planar_kernel<E, HAS_GRAD, STAGES, NOUT, SIG>;
   YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int dev = 0, sms = kNumSMs, per_sm = 1;
   YOLO1_CUDA_TRY(cudaGetDevice(&dev));
@@ -826,8 +880,12 @@ template <typename E, bool HAS_GRAD>
 int launch_planar(const LossParams& p, int tile_imgs, cudaStream_t stream) {
   const size_t tile_cells = (size_t)tile_imgs * p.S * p.S;
   const size_t separate = 2 * tile_cells * 30 * (sizeof(E) + 4) + 2 * tile_cells * 30 * sizeof(E);
-  if (separate <= 110 * 1024) return launch_planar_n<E, HAS_GRAD, 2>(p, tile_imgs, stream);
-  return launch_planar_n<E, HAS_GRAD, 0>(p, tile_imgs, stream);
+  if (p.logits) {
+    if (separate <= 110 * 1024) return launch_planar_n<E, HAS_GRAD, 2, true>(p, tile_imgs, stream);
+    return launch_planar_n<E, HAS_GRAD, 0, true>(p, tile_imgs, stream);
+  }
+  if (separate <= 110 * 1024) return launch_planar_n<E, HAS_GRAD, 2, false>(p, tile_imgs, stream);
+  return launch_planar_n<E, HAS_GRAD, 0, false>(p, tile_imgs, stream);
 }
 
 template <bool HAS_GRAD>
@@ -864,7 +922,7 @@ int launch_generic(const LossParams& p, cudaStream_t stream) {
 }  // namespace
 
 // Launches one chunk of a loss call.  chunk_flags: bit 0 = first chunk (resets the workspace), bit 1 = last
-// chunk (writes terms).  variant < 0 forces the generic kernel.  Used by the public entry points below and by
+// chunk (writes terms), bit 2 = pred holds pre-sigmoid logits (fused head epilogue).  variant < 0 forces the generic kernel.  Used by the public entry points below and by
 // the host-buffer pipeline (host_ctx.cu).
 int loss_launch_chunk(const void* pred, const int64_t ps[4], int pred_dtype, const float* target,
                       const int64_t ts[4], void* grad, const int64_t gs[4], float* terms, int64_t N, int S,
@@ -891,7 +949,7 @@ int loss_launch_chunk(const void* pred, const int64_t ps[4], int pred_dtype, con
   p.cells = cells, p.S = S, p.B = B, p.C = C;
   p.Sf = (float)S, p.lc = lambda_coord, p.ln = lambda_noobj, p.inv_bs = inv_batch_size;
   p.k2ln = 2.0f * lambda_noobj * inv_batch_size, p.k2 = 2.0f * inv_batch_size;
-  p.coord_mode = coord_mode, p.last_chunk = (chunk_flags & 2) ? 1 : 0;
+  p.coord_mode = coord_mode, p.last_chunk = (chunk_flags & 2) ? 1 : 0, p.logits = (chunk_flags & 4) ? 1 : 0;
 
   if (chunk_flags & 1) YOLO1_CUDA_TRY(cudaMemsetAsync(workspace, 0, offsetof(LossWs, partial), stream));
 
@@ -901,7 +959,7 @@ int loss_launch_chunk(const void* pred, const int64_t ps[4], int pred_dtype, con
                     (!grad || (uintptr_t)grad % 16 == 0);
   const bool bf = pred_dtype == YOLO1_DTYPE_BF16;
   if (variant == kVariantHostMapped) {  // pointers are device-visible HOST memory (host_ctx.cu)
-    if (!fast || bf) return YOLO1_ERR_UNSUPPORTED;
+    if (!fast || bf || p.logits) return YOLO1_ERR_UNSUPPORTED;
     return grad ? launch_hostmapped<true>(p, stream) : launch_hostmapped<false>(p, stream);
   }
   if (fast) {
@@ -947,6 +1005,16 @@ int yolo1_loss_fwd_bwd_ex(const void* pred, const int64_t pred_strides[4], int p
   return yolo1::loss_launch_chunk(pred, pred_strides, pred_dtype, target, target_strides, grad, grad_strides,
                                   terms, N, S, B, C, lambda_coord, lambda_noobj, inv_batch_size, coord_mode,
                                   workspace, workspace_bytes, 3, variant, (cudaStream_t)stream);
+}
+
+int yolo1_loss_fwd_bwd_logits(const void* logits, const int64_t logit_strides[4], int dtype, const float* target,
+                              const int64_t target_strides[4], void* grad, const int64_t grad_strides[4],
+                              float* terms, int64_t N, int S, int B, int C, float lambda_coord, float lambda_noobj,
+                              float inv_batch_size, int coord_mode, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  return yolo1::loss_launch_chunk(logits, logit_strides, dtype, target, target_strides, grad, grad_strides, terms, N,
+                                  S, B, C, lambda_coord, lambda_noobj, inv_batch_size, coord_mode, workspace,
+                                  workspace_bytes, 3 | 4, 0, (cudaStream_t)stream);
 }
 
 int yolo1_scale_grad(void* grad, int dtype, int64_t storage_numel, const float* grad_out_dev, void* stream) {

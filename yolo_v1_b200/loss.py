@@ -34,7 +34,7 @@ def _stream_ptr(device):
 
 def yolo_loss_fused(pred, target, batch_size, S=None, B=2, C=20, l_coord=5.0, l_noobj=0.5,
                     coord_mode="reference", want_grad=True, variant=0, out_grad=None, out_terms=None,
-                    workspace=None):
+                    workspace=None, from_logits=False):
     """One fused pass: loss terms AND d total / d pred (v1Loss.py:22-118 + its autograd backward).
 
     pred  : CUDA tensor [N,S,S,5B+C], float32 or bfloat16, ANY strides (the backbone's permuted NCHW view,
@@ -43,6 +43,8 @@ def yolo_loss_fused(pred, target, batch_size, S=None, B=2, C=20, l_coord=5.0, l_
     Returns (loss, grad, terms): loss = terms[4] (0-dim view), grad laid out like pred (or None),
     terms = float32[5] on the device: location, contain, not_contain, classify (each / batch_size, the four
     numbers v1Loss.py:108 logs) and the total.  Stream ordered on the current stream; no host sync.
+    from_logits=True: `pred` holds the head's PRE-sigmoid outputs (OriginResNet.py:186-188); the sigmoid is applied
+    inside the kernel and `grad` is d total / d logit (yolo1_loss_fwd_bwd_logits).
     """
     if pred.dim() != 4 or pred.shape != target.shape:
         raise ValueError("pred and target must both be [N,S,S,5B+C]; got %s and %s" %
@@ -72,14 +74,16 @@ def yolo_loss_fused(pred, target, batch_size, S=None, B=2, C=20, l_coord=5.0, l_
         ws = workspace if workspace is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         if ws.numel() * ws.element_size() < ws_bytes:
             raise ValueError("workspace too small: need %d bytes" % ws_bytes)
-        rc = L.yolo1_loss_fwd_bwd_ex(
-            pred.data_ptr(), _lib.strides4(pred), _dtype_code(pred),
-            target.data_ptr(), _lib.strides4(target),
-            grad.data_ptr() if grad is not None else None,
-            _lib.strides4(grad) if grad is not None else None,
-            terms.data_ptr(), N, S, B, C, float(l_coord), float(l_noobj), 1.0 / float(batch_size),
-            _COORD_MODES[coord_mode], ws.data_ptr(), ws.numel() * ws.element_size(), int(variant),
-            _stream_ptr(dev))
+        common = (pred.data_ptr(), _lib.strides4(pred), _dtype_code(pred),
+                  target.data_ptr(), _lib.strides4(target),
+                  grad.data_ptr() if grad is not None else None,
+                  _lib.strides4(grad) if grad is not None else None,
+                  terms.data_ptr(), N, S, B, C, float(l_coord), float(l_noobj), 1.0 / float(batch_size),
+                  _COORD_MODES[coord_mode], ws.data_ptr(), ws.numel() * ws.element_size())
+        if from_logits:
+            rc = L.yolo1_loss_fwd_bwd_logits(*common, _stream_ptr(dev))
+        else:
+            rc = L.yolo1_loss_fwd_bwd_ex(*common, int(variant), _stream_ptr(dev))
         _lib.check(rc, "yolo1_loss_fwd_bwd")
     return terms[4], grad, terms
 
@@ -139,14 +143,15 @@ class YOLOLossV1(nn.Module):
       * nothing is printed per call unless `_logger`/`_vis` are given or `verbose=True`
         (the reference prints four numbers on every call, v1Loss.py:110, forcing host syncs);
       * keyword-only extras: `coord_mode` ('reference' = the row-slice behaviour of v1Loss.py:101,
-        'paper' = xy plain / wh sqrt), `verbose`.
+        'paper' = xy plain / wh sqrt), `verbose`, `from_logits` (feed the head's pre-sigmoid output; the
+        sigmoid of OriginResNet.py:188 and its backward are fused into the loss kernel).
     `_device` is accepted for signature compatibility; tensors are used where they live.  Host (CPU)
     tensors are staged through the pipelined host-buffer path of the library (no CPU arithmetic).
     The module has no parameters or buffers (state_dict() of an enclosing model is unchanged).
     """
 
     def __init__(self, _batch_size, _S, _B, _clsN, _l_coord=5., _l_noobj=0.5, _device='cuda:0', _logger=None,
-                 _vis=None, *, coord_mode="reference", verbose=False):
+                 _vis=None, *, coord_mode="reference", verbose=False, from_logits=False):
         super().__init__()
         if coord_mode not in _COORD_MODES:
             raise ValueError("coord_mode must be 'reference' or 'paper'")
@@ -161,12 +166,13 @@ class YOLOLossV1(nn.Module):
         self.vis = _vis
         self.coord_mode = coord_mode
         self.verbose = verbose
+        self.from_logits = from_logits   # inputs are pre-sigmoid head outputs: sigmoid fused into the kernel
         self.last_terms = None   # device float32[5] of the latest call (read lazily: no sync unless asked)
         self._host_ctx = None
 
     def _cfg(self):
         return dict(batch_size=self.batch_size, S=self.S, B=self.B, C=self.C, l_coord=self.lambda_coord,
-                    l_noobj=self.lambda_noobj, coord_mode=self.coord_mode)
+                    l_noobj=self.lambda_noobj, coord_mode=self.coord_mode, from_logits=self.from_logits)
 
     def forward(self, pred_tensor, target_tensor):
         if pred_tensor.is_cuda:
@@ -179,6 +185,8 @@ class YOLOLossV1(nn.Module):
         return loss
 
     def _forward_host(self, pred, target):
+        if self.from_logits:
+            raise RuntimeError("from_logits=True needs CUDA tensors")
         if self._host_ctx is None:
             self._host_ctx = _host.HostContext(self.S, self.B, self.C)
         return _HostYoloLoss.apply(pred, target, self._host_ctx, self._cfg())
