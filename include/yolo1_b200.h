@@ -106,6 +106,34 @@ YOLO1_API int yolo1_loss_fwd_bwd_logits(const void* logits, const int64_t logit_
                                         void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Loss straight from object lists -- the dense target tensor is never materialised.
+ * boxes [n_obj,4] (cx,cy,w,h normalised to the image; 16-byte aligned), labels [n_obj], offsets [N+1] (CSR) are
+ * what yoloDataset.encoder (utils/YOLODataLoader.py:200-230) would be fed per image; the call computes exactly
+ * yolo1_loss_fwd_bwd(pred, encoder(boxes, labels), ...) (or ..._logits when from_logits != 0) but reads
+ * 4 bytes per cell (the index of the owning object) instead of a 120-byte target row: 248 instead of 360
+ * algorithmic bytes per cell.  workspace: yolo1_loss_objects_workspace_bytes(N,S,B,C) bytes, 16-byte aligned
+ * (header + per-CTA partials + the N*S*S int32 cell map).  status: device int32, 1 if a centre / label was
+ * outside the grid / class range (the reference raises IndexError; such objects are skipped), else 0.
+ */
+YOLO1_API size_t yolo1_loss_objects_workspace_bytes(int64_t N, int S, int B, int C);
+YOLO1_API int yolo1_loss_fwd_bwd_objects(const void* pred, const int64_t pred_strides[4], int pred_dtype,
+                                         int from_logits, const float* boxes, const int32_t* labels,
+                                         const int64_t* offsets, void* grad, const int64_t grad_strides[4],
+                                         float* terms, int64_t N, int S, int B, int C,
+                                         float lambda_coord, float lambda_noobj, float inv_batch_size,
+                                         int coord_mode, void* workspace, size_t workspace_bytes, int32_t* status,
+                                         void* stream);
+
+/* Tuning twin of yolo1_loss_fwd_bwd_objects: `variant` as in yolo1_loss_fwd_bwd_ex. */
+YOLO1_API int yolo1_loss_fwd_bwd_objects_ex(const void* pred, const int64_t pred_strides[4], int pred_dtype,
+                                            int from_logits, const float* boxes, const int32_t* labels,
+                                            const int64_t* offsets, void* grad, const int64_t grad_strides[4],
+                                            float* terms, int64_t N, int S, int B, int C,
+                                            float lambda_coord, float lambda_noobj, float inv_batch_size,
+                                            int coord_mode, void* workspace, size_t workspace_bytes,
+                                            int32_t* status, int variant, void* stream);
+
+/*
  * grad *= *grad_out_dev, in place, for autograd's backward(grad_output) (train.py:171 calls
  * loss.backward() with grad_output = 1; AMP loss scaling makes it != 1).  The kernel reads the scalar
  * on the device and returns without touching memory when it is exactly 1.0f, so the usual training

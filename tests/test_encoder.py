@@ -81,3 +81,55 @@ def test_cuda_encoder_large_random_batches_vs_oracle_and_loss_consumes_it():
     t = y.encode_targets(torch.zeros(0, 4).cuda(), torch.zeros(0, dtype=torch.int32).cuda(),
                          torch.zeros(5, dtype=torch.int64).cuda(), 7)
     assert t.shape == (4, 7, 7, 30) and float(t.abs().sum()) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["nhwc", "planar", "strided"])
+@pytest.mark.parametrize("dtype,logits", [("f32", False), ("bf16", False), ("f32", True)])
+def test_loss_from_object_lists_equals_loss_on_encoded_target(layout, dtype, logits):
+    """yolo1_loss_fwd_bwd_objects == yolo1_loss_fwd_bwd(pred, encoder(lists)): same gradient bit for bit, same
+    terms (up to the summation order of a different grid), and both match the oracle."""
+    import yolo_v1_b200 as y
+    rng = np.random.RandomState(11)
+    for S, N in [(7, 131), (14, 37), (7, 2)]:
+        counts = rng.randint(0, 6, size=N)
+        counts[0] = 0                                     # first image empty: the call's first objects come later
+        offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        boxes = rng.rand(int(offsets[-1]), 4).astype(np.float32)
+        boxes[:, 2:] = boxes[:, 2:] * 0.8 + 0.05
+        if len(boxes) > 3:
+            boxes[1, :2] = boxes[0, :2]                   # collision: the last object in a cell wins
+            boxes[2, :2] = [0.0, 1.0]                     # Python -1 indexing / edge
+        labels = rng.randint(0, 20, size=int(offsets[-1])).astype(np.int32)
+        dense = O.encode(boxes, labels, offsets, S)
+        g = torch.Generator().manual_seed(S + N)
+        pred = torch.randn(N, S, S, 30, generator=g) * 1.5 if logits else torch.rand(N, S, S, 30, generator=g) * 0.98 + 0.01
+        if dtype == "bf16":
+            pred = pred.to(torch.bfloat16)
+        pc = pred.cuda()
+        if layout == "planar":
+            pc = pc.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+        elif layout == "strided":
+            pc = torch.zeros(N, S, S, 32, dtype=pred.dtype, device="cuda")[..., :30].copy_(pred)
+        b, l, o = torch.from_numpy(boxes).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(offsets).cuda()
+        _, g1, t1 = y.yolo_loss_from_objects(pc, b, l, o, batch_size=N, from_logits=logits, check=True)
+        _, g2, t2 = y.yolo_loss_fused(pc, torch.from_numpy(dense).cuda(), batch_size=N, from_logits=logits)
+        assert torch.equal(g1, g2), (S, N, layout, dtype, logits)
+        assert torch.allclose(t1, t2, rtol=2e-6, atol=1e-7)
+        _, _, t3 = y.yolo_loss_from_objects(pc, b, l, o, batch_size=N, from_logits=logits, want_grad=False)
+        assert torch.allclose(t3, t1, rtol=2e-6, atol=1e-7)
+        if not logits and dtype == "f32":
+            o_terms, o_grad = O.loss(pred.numpy(), dense, batch_size=N)
+            assert np.allclose(t1.cpu().numpy(), o_terms, rtol=1e-5)
+            assert np.abs(g1.cpu().numpy() - o_grad).max() <= 1e-5 * max(np.abs(o_grad).max(), 1e-12)
+    # module form with autograd; out-of-grid centre -> IndexError with check=True
+    mod = y.YOLOLossV1(4, 7, 2, 20)
+    p = torch.rand(4, 7, 7, 30, device="cuda", requires_grad=True)
+    bx, lb, of = y.pack_objects([torch.tensor([[0.3, 0.3, 0.2, 0.2]]), torch.zeros(0, 4), torch.tensor([[0.9, 0.1, 0.1, 0.1]]),
+                                 torch.zeros(0, 4)], [torch.tensor([1]), torch.zeros(0), torch.tensor([2]), torch.zeros(0)])
+    mod.forward_objects(p, bx, lb, of).backward()
+    want = y.yolo_loss_fused(p.detach(), y.encode_targets(bx, lb, of), batch_size=4)[1]
+    assert torch.equal(p.grad, want)
+    with pytest.raises(IndexError):
+        y.yolo_loss_from_objects(p.detach(), torch.tensor([[1.5, 0.5, 0.1, 0.1]]).cuda(), torch.tensor([0]).cuda(),
+                                 torch.tensor([0, 1, 1, 1, 1]).cuda(), batch_size=4, check=True)

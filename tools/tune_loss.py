@@ -44,3 +44,34 @@ for name, p, g, variants in (("nhwc", pred, grad, [0, 5, 8, 9, 10, 11, 12, 13]),
             b = cells * (bytes_per_cell if want_grad else bytes_per_cell - 30 * pred.element_size())
             print("%-12s variant %2d grad=%d  median %.3f ms  min %.3f ms  %.2f Gcells/s  %.0f GB/s (%.3f of measured %.0f)"
                   % (name, v, want_grad, med, ts[0], cells / med / 1e6, b / med / 1e6, b / med / 1e6 / peak, peak), flush=True)
+
+# ---- loss from object lists (no dense target): 248 algorithmic bytes per cell (fp32) ----
+tgt_cells = (target[..., 0] == 1)
+cnt = tgt_cells.reshape(N, -1).sum(1)
+offsets = torch.zeros(N + 1, dtype=torch.int64, device="cuda")
+offsets[1:] = cnt.cumsum(0)
+idx = tgt_cells.nonzero()                                   # (n, i, j) row-major = input order per image
+bx = target[idx[:, 0], idx[:, 1], idx[:, 2], 2:6]
+cxcy = (bx[:, :2] + torch.stack([idx[:, 2], idx[:, 1]], 1).float()) / S
+boxes_l = torch.cat([cxcy, bx[:, 2:]], 1).contiguous()
+labels_l = target[idx[:, 0], idx[:, 1], idx[:, 2], 10:].argmax(1).to(torch.int32)
+ws2 = torch.empty(int(y._lib.lib().yolo1_loss_objects_workspace_bytes(N, S, 2, 20)), dtype=torch.uint8, device="cuda")
+for name, p, v in (("nhwc", pred, 0), ("nhwc", pred, 2), ("nhwc", pred, 3), ("nhwc", pred, 4), ("nhwc", pred, 6), ("planar-view", planar, 0)):
+    def run():
+        y.yolo_loss_from_objects(p, boxes_l, labels_l, offsets, batch_size=N, variant=v, out_grad=grad if p is pred else gplanar, workspace=ws2)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    med = ts[5]
+    b = cells * (30 * 2 * pred.element_size() + 8)
+    print("%-12s object-list targets v%d median %.3f ms  min %.3f ms  %.2f Gcells/s  %.0f GB/s of 248-byte cells (%.3f of measured)"
+          % (name, v, med, ts[0], cells / med / 1e6, b / med / 1e6, b / med / 1e6 / peak), flush=True)

@@ -5,7 +5,7 @@ Drop-in for the reference's call surface (haoran1062/YOLO_V1):
 The arithmetic lives in libyolo1_b200.so (C ABI: include/yolo1_b200.h, sources: yolo_v1_b200/csrc/); there is
 no CPU fallback -- entry points raise if the library has not been built.
 """
-from .loss import YOLOLossV1, yolo_loss_fused, scale_grad_          # noqa: F401
+from .loss import YOLOLossV1, yolo_loss_fused, yolo_loss_from_objects, scale_grad_   # noqa: F401
 from .decode import (decoder, nms, decode_nms_batched, decode_batched, nms_batched,   # noqa: F401
                      compute_iou_matrix, convert_CxCyWH_to_X1Y1X2Y2)
 from .voc import voc_eval, voc_ap, run_test_mAP, detections_to_voc_preds, boxes_to_pixels, VOC_CLASSES  # noqa: F401

@@ -35,6 +35,15 @@ SIGNATURES = {
                                              _c.c_int64, _c.c_int, _c.c_int, _c.c_int,
                                              _c.c_float, _c.c_float, _c.c_float, _c.c_int,
                                              _vp, _c.c_size_t, _vp]),
+    "yolo1_loss_objects_workspace_bytes": (_c.c_size_t, [_c.c_int64, _c.c_int, _c.c_int, _c.c_int]),
+    "yolo1_loss_fwd_bwd_objects": (_c.c_int, [_vp, _i64p, _c.c_int, _c.c_int, _vp, _vp, _vp, _vp, _i64p, _vp,
+                                              _c.c_int64, _c.c_int, _c.c_int, _c.c_int,
+                                              _c.c_float, _c.c_float, _c.c_float, _c.c_int,
+                                              _vp, _c.c_size_t, _vp, _vp]),
+    "yolo1_loss_fwd_bwd_objects_ex": (_c.c_int, [_vp, _i64p, _c.c_int, _c.c_int, _vp, _vp, _vp, _vp, _i64p, _vp,
+                                                 _c.c_int64, _c.c_int, _c.c_int, _c.c_int,
+                                                 _c.c_float, _c.c_float, _c.c_float, _c.c_int,
+                                                 _vp, _c.c_size_t, _vp, _c.c_int, _vp]),
     "yolo1_scale_grad": (_c.c_int, [_vp, _c.c_int, _c.c_int64, _vp, _vp]),
     "yolo1_decode": (_c.c_int, [_vp, _i64p, _c.c_int, _c.c_int64, _c.c_int, _c.c_int, _c.c_int,
                                 _c.c_double, _vp, _vp, _vp, _vp, _vp]),

@@ -102,6 +102,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// The reference encoder's arithmetic for one box centre (utils/YOLODataLoader.py:218-224), every operation
+// rounded on its own (explicit intrinsics: valid in translation units built with or without -fmad=false):
+//   idx = ceil(c / fl32(1/S)) - 1 ;  delta = (c - idx * fl32(1/S)) / fl32(1/S)
+__device__ __forceinline__ void encode_axis(float c, float cs, float& fidx, float& delta) {
+  fidx = __fsub_rn(ceilf(__fdiv_rn(c, cs)), 1.0f);
+  delta = __fdiv_rn(__fsub_rn(c, __fmul_rn(fidx, cs)), cs);
+}
+
 // element load/store with on-the-fly bf16 <-> fp32 conversion
 __device__ __forceinline__ float ld_elem(const float* p) { return *p; }
 __device__ __forceinline__ float ld_elem(const __nv_bfloat16* p) { return __bfloat162float(*p); }

@@ -42,7 +42,9 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Enc
       const int64_t k0 = p.offsets[g0 + threadIdx.x], k1 = p.offsets[g0 + threadIdx.x + 1];
       for (int64_t k = k0; k < k1; ++k) {
         const float cx = p.boxes[4 * k], cy = p.boxes[4 * k + 1], w = p.boxes[4 * k + 2], h = p.boxes[4 * k + 3];
-        const float fi = ceilf(__fdiv_rn(cx, p.cs)) - 1.0f, fj = ceilf(__fdiv_rn(cy, p.cs)) - 1.0f;  // :218-219
+        float fi, fj, dx, dy;
+        encode_axis(cx, p.cs, fi, dx);  // :218-219, :223-224
+        encode_axis(cy, p.cs, fj, dy);
         int col = (int)fi, row = (int)fj, lab = p.labels[k];
         if (col < -S || col >= S || row < -S || row >= S || lab < -C || lab >= C) {  // reference: IndexError
           atomicExch(p.status, 1);
@@ -53,7 +55,6 @@ __global__ void __launch_bounds__(256) encode_kernel(const __grid_constant__ Enc
         if (lab < 0) lab += C;
         float* t = timg + (row * S + col) * D;
         for (int c = 0; c < D; ++c) t[c] = 0.f;  // :220 reset -> the last object in a cell wins
-        const float dx = __fdiv_rn(cx - fi * p.cs, p.cs), dy = __fdiv_rn(cy - fj * p.cs, p.cs);  // :223-224
         for (int b = 0; b < B; ++b) {
           t[b] = 1.f;  // :221
           t[B + 4 * b] = dx, t[B + 4 * b + 1] = dy, t[B + 4 * b + 2] = w, t[B + 4 * b + 3] = h;  // :225-227

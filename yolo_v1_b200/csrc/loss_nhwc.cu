@@ -1,0 +1,179 @@
+// loss_nhwc.cu -- K1 streaming kernel for contiguous [N,S,S,30] tensors (see loss_common.cuh for the design).
+#include "loss_common.cuh"
+
+namespace yolo1 {
+namespace {
+
+// ---- K1 fast kernel: contiguous layout, TMA in / TMA out ----------------------------------------------
+template <typename E, bool HAS_GRAD, int TILE, int STAGES, int NOUT, bool SIG = false, bool LIST = false>
+__global__ void __launch_bounds__(TILE) loss_tma_kernel(const __grid_constant__ LossParams p) {
+  constexpr int D = 30;
+  // LIST: the target stage holds one int per cell (the owning object's index) instead of 30 floats
+  constexpr uint32_t PB = TILE * D * sizeof(E), TB = LIST ? TILE * sizeof(int32_t) : TILE * D * sizeof(float), GB = PB;
+  static_assert(PB % 16 == 0 && TB % 16 == 0, "bulk copies move multiples of 16 bytes");
+  static_assert(NOUT == 0 || NOUT >= 2, "NOUT = 0: gradient tile overwrites the pred stage in place; else >= 2 buffers");
+  constexpr bool INPLACE = NOUT == 0;
+  extern __shared__ __align__(128) unsigned char smem[];
+  E* sp = reinterpret_cast<E*>(smem);
+  float* st = reinterpret_cast<float*>(smem + STAGES * PB);
+  E* so = reinterpret_cast<E*>(smem + STAGES * (PB + TB));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (PB + TB) + NOUT * GB);
+
+  const int tid = threadIdx.x;
+  const int64_t full = p.cells / TILE;  // tiles moved by the copy engine; the ragged tail goes direct
+  const int64_t my_n = full > (int64_t)blockIdx.x ? (full - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const E* gp = reinterpret_cast<const E*>(p.pred);
+  E* gg = reinterpret_cast<E*>(p.grad);
+  uint64_t pol = 0;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+    pol = policy_evict_first();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t k) {
+    const int s = (int)(k % STAGES);
+    const int64_t off = ((int64_t)blockIdx.x + k * gridDim.x) * (TILE * D);
+    mbar_arrive_expect_tx(&bars[s], PB + ((LIST && k + 1 >= my_n) ? 0u : TB));
+    bulk_g2s(sp + s * (TILE * D), gp + off, PB, &bars[s], pol);
+    if (LIST) {
+      // the stage of tile k carries the ownership map of tile k+1 (see the software pipeline below)
+      if (k + 1 < my_n)
+        bulk_g2s(reinterpret_cast<unsigned char*>(st) + s * TB,
+                 p.cellobj + ((int64_t)blockIdx.x + (k + 1) * gridDim.x) * TILE, TB, &bars[s], pol);
+    } else {
+      bulk_g2s(st + s * (TILE * D), p.target + off, TB, &bars[s], pol);
+    }
+  };
+  if (tid == 0)
+    for (int64_t k = 0; k < my_n && k < STAGES; ++k) issue(k);
+
+  CellSums sums = {0.f, 0.f, 0.f, 0.f};
+  uint32_t m1 = 0, m2 = 0;
+  // LIST: the object record of my cell in the NEXT tile, fetched while the current tile is being finished
+  ObjFetch nxt = {make_float4(0.f, 0.f, 0.f, 0.f), 0, -1};
+  if (LIST && my_n > 0) nxt = fetch_object(p, p.cellobj[(int64_t)blockIdx.x * TILE + tid]);
+  using PIn = typename SmemIn<E>::type;
+  using GOut = typename SmemOut<E>::type;
+  for (int64_t k = 0; k < my_n; ++k) {
+    const int s = (int)(k % STAGES), o = INPLACE ? 0 : (int)(k % (NOUT > 0 ? NOUT : 1));
+    mbar_wait(&bars[s], (uint32_t)((k / STAGES) & 1));
+    const PIn P{sp + s * (TILE * D) + tid * D};
+    const SmemInF32 T{st + s * (TILE * D) + tid * D};
+    // in-place: every thread reads its own cell's 30 values before it overwrites them with the gradient
+    E* gtile = INPLACE ? sp + s * (TILE * D) : so + o * (TILE * D);
+    const GOut G{gtile + tid * D};
+    bool obj;
+    if (LIST) {
+      const ListTarget2 TL = list_target2(p, nxt);
+      if (k + 1 < my_n) {  // gather for tile k+1 now; it lands behind the barrier and the next wait
+        const int32_t* slots = reinterpret_cast<const int32_t*>(reinterpret_cast<const unsigned char*>(st) + s * TB);
+        nxt = fetch_object(p, slots[tid]);
+      }
+      if (SIG)
+        obj = cell_b2c20<HAS_GRAD>(SigIn<PIn>{P}, TL, SigOut<GOut, PIn>{G, P}, p, sums);
+      else
+        obj = cell_b2c20<HAS_GRAD>(P, TL, G, p, sums);
+    } else if (SIG) {
+      obj = cell_b2c20<HAS_GRAD>(SigIn<PIn>{P}, T, SigOut<GOut, PIn>{G, P}, p, sums);
+    } else {
+      obj = cell_b2c20<HAS_GRAD>(P, T, G, p, sums);
+    }
+    if (obj) note_object(m1, m2, ((int64_t)blockIdx.x + k * gridDim.x) * TILE + tid);
+    if (HAS_GRAD) {
+      fence_async_smem();  // my shared-memory gradient writes -> visible to the copy engine
+      if (!INPLACE && tid == 0) bulk_wait_read<(NOUT >= 2 ? NOUT - 2 : 0)>();  // buffer (k+1) % NOUT is free again
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (HAS_GRAD) {
+        bulk_s2g(gg + ((int64_t)blockIdx.x + k * gridDim.x) * (TILE * D), gtile, GB, pol);
+        bulk_commit();
+      }
+      if (k + STAGES < my_n) {
+        if (HAS_GRAD && INPLACE) bulk_wait_read<0>();  // the store has drained stage s: it may be refilled
+        issue(k + STAGES);
+      }
+    }
+  }
+  // ragged tail (< TILE cells): one CTA, straight from / to global memory
+  const int64_t tail0 = full * TILE;
+  if ((int64_t)blockIdx.x == full % gridDim.x && tail0 + tid < p.cells) {
+    const int64_t q = tail0 + tid;
+    const GlobIn<E> P{gp + q * D, 1, SIG};
+    const GlobOut<E> G{HAS_GRAD ? gg + q * D : nullptr, 1, gp + q * D, 1, SIG};
+    bool obj;
+    if (LIST) {
+      obj = cell_generic<HAS_GRAD, false>(P, list_targetS(p, q), G, p, sums);
+    } else {
+      const GlobIn<float> T{p.target + q * D, 1, false};
+      obj = cell_generic<HAS_GRAD, false>(P, T, G, p, sums);
+    }
+    if (obj) note_object(m1, m2, q);
+  }
+  block_epilogue<E, HAS_GRAD, true>(sums, m1, m2, p);
+}
+
+template <typename E, bool HAS_GRAD, int TILE, int STAGES, int NOUT, bool SIG = false, bool LIST = false>
+int launch_tma(const LossParams& p, cudaStream_t stream) {
+  constexpr size_t smem = (size_t)STAGES * TILE * (30 * sizeof(E) + (LIST ? 4 : 120)) +
+                          (size_t)NOUT * TILE * 30 * sizeof(E) + STAGES * sizeof(uint64_t);
+  auto kern = loss_tma_kernel<E, HAS_GRAD, TILE, STAGES, NOUT, SIG, LIST>;
+  YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = kNumSMs, per_sm = 1;
+  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
+  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  YOLO1_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t tiles = p.cells / TILE;
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > tiles) grid = tiles;
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, TILE, smem, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
+template <typename E, bool HAS_GRAD>
+int launch_tma_variant(const LossParams& p, int variant, cudaStream_t stream) {
+  if (p.list_mode) {  // object-list targets
+    if (p.logits) return launch_tma<E, HAS_GRAD, 128, 2, 2, true, true>(p, stream);
+    switch (variant) {
+      case 3: return launch_tma<E, HAS_GRAD, 64, 3, 2, false, true>(p, stream);
+      case 4: return launch_tma<E, HAS_GRAD, 64, 4, 3, false, true>(p, stream);
+      case 6: return launch_tma<E, HAS_GRAD, 32, 4, 2, false, true>(p, stream);
+      case 2: return launch_tma<E, HAS_GRAD, 128, 3, 2, false, true>(p, stream);
+      default: return launch_tma<E, HAS_GRAD, 128, 2, 2, false, true>(p, stream);
+    }
+  }
+  if (p.logits) return launch_tma<E, HAS_GRAD, 128, 2, 2, true>(p, stream);  // one launch shape with the fused head
+  switch (variant) {
+    case 0:
+    case 1: return launch_tma<E, HAS_GRAD, 128, 2, 2>(p, stream);
+    case 2: return launch_tma<E, HAS_GRAD, 128, 3, 2>(p, stream);
+    case 3: return launch_tma<E, HAS_GRAD, 64, 3, 2>(p, stream);
+    case 4: return launch_tma<E, HAS_GRAD, 64, 4, 3>(p, stream);
+    case 5: return launch_tma<E, HAS_GRAD, 256, 2, 2>(p, stream);
+    case 6: return launch_tma<E, HAS_GRAD, 32, 4, 2>(p, stream);
+    case 7: return launch_tma<E, HAS_GRAD, 32, 6, 3>(p, stream);
+    case 8: return launch_tma<E, HAS_GRAD, 128, 2, 0>(p, stream);   // in-place gradient tile: 61 KB, 3 CTAs/SM
+    case 9: return launch_tma<E, HAS_GRAD, 128, 3, 0>(p, stream);   // 92 KB, 2 CTAs/SM
+    case 10: return launch_tma<E, HAS_GRAD, 192, 2, 0>(p, stream);  // 92 KB, 2 CTAs/SM
+    case 11: return launch_tma<E, HAS_GRAD, 96, 2, 0>(p, stream);   // 46 KB, 4 CTAs/SM
+    case 12: return launch_tma<E, HAS_GRAD, 64, 2, 0>(p, stream);   // 31 KB, 7 CTAs/SM
+    case 13: return launch_tma<E, HAS_GRAD, 256, 2, 0>(p, stream);  // 123 KB, 1 CTA/SM
+    default: return YOLO1_ERR_ARG;
+  }
+}
+
+}  // namespace
+
+int launch_loss_nhwc(const LossParams& p, bool bf16, bool has_grad, int variant, cudaStream_t stream) {
+  if (bf16) return has_grad ? launch_tma_variant<__nv_bfloat16, true>(p, variant, stream)
+                            : launch_tma_variant<__nv_bfloat16, false>(p, variant, stream);
+  return has_grad ? launch_tma_variant<float, true>(p, variant, stream)
+                  : launch_tma_variant<float, false>(p, variant, stream);
+}
+
+}  // namespace yolo1

@@ -14,7 +14,7 @@ import torch.nn as nn
 from . import _lib
 from . import host as _host
 
-__all__ = ["YOLOLossV1", "yolo_loss_fused", "scale_grad_"]
+__all__ = ["YOLOLossV1", "yolo_loss_fused", "yolo_loss_from_objects", "scale_grad_"]
 
 _COORD_MODES = {"reference": _lib.COORD_REFERENCE, "paper": _lib.COORD_PAPER}
 TERM_NAMES = ("location", "contain", "not_contain", "classify", "total")
@@ -88,6 +88,48 @@ def yolo_loss_fused(pred, target, batch_size, S=None, B=2, C=20, l_coord=5.0, l_
     return terms[4], grad, terms
 
 
+def yolo_loss_from_objects(pred, boxes, labels, offsets, batch_size, S=None, B=2, C=20, l_coord=5.0, l_noobj=0.5,
+                           coord_mode="reference", want_grad=True, from_logits=False, out_grad=None, check=False,
+                           variant=0, workspace=None):
+    """The fused loss fed with object lists instead of a dense target (yolo1_loss_fwd_bwd_objects):
+    identical to `yolo_loss_fused(pred, encode_targets(boxes, labels, offsets), ...)` without ever writing or
+    reading the [N,S,S,5B+C] target -- boxes [n,4] (cx,cy,w,h), labels [n], offsets [N+1] CUDA tensors in the CSR
+    form of `pack_objects`.  Returns (loss, grad, terms).  check=True costs one host sync and raises IndexError
+    when a box centre / label lies outside the grid / class range (as the reference encoder would)."""
+    if not pred.is_cuda:
+        raise RuntimeError("yolo_loss_from_objects needs CUDA tensors")
+    N, S_, S2, D = pred.shape
+    if S is None:
+        S = S_
+    if S_ != S or S2 != S or D != 5 * B + C or offsets.shape[0] != N + 1:
+        raise ValueError("shapes do not match: pred %s, offsets %s, S=%d B=%d C=%d" %
+                         (tuple(pred.shape), tuple(offsets.shape), S, B, C))
+    dev = pred.device
+    boxes = boxes.to(device=dev, dtype=torch.float32).contiguous().reshape(-1, 4)
+    labels = labels.to(device=dev, dtype=torch.int32).contiguous().reshape(-1)
+    offsets = offsets.to(device=dev, dtype=torch.int64).contiguous()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        grad = None
+        if want_grad:
+            grad = out_grad if out_grad is not None else torch.empty_like(pred)
+        terms = torch.empty(5, dtype=torch.float32, device=dev)
+        status = torch.empty(1, dtype=torch.int32, device=dev)
+        ws_bytes = int(L.yolo1_loss_objects_workspace_bytes(N, S, B, C))
+        ws = workspace if workspace is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rc = L.yolo1_loss_fwd_bwd_objects_ex(
+            pred.data_ptr(), _lib.strides4(pred), _dtype_code(pred), int(bool(from_logits)),
+            boxes.data_ptr() if boxes.numel() else None, labels.data_ptr() if labels.numel() else None,
+            offsets.data_ptr(), grad.data_ptr() if grad is not None else None,
+            _lib.strides4(grad) if grad is not None else None, terms.data_ptr(), N, S, B, C,
+            float(l_coord), float(l_noobj), 1.0 / float(batch_size), _COORD_MODES[coord_mode],
+            ws.data_ptr(), ws_bytes, status.data_ptr(), int(variant), _stream_ptr(dev))
+        _lib.check(rc, "yolo1_loss_fwd_bwd_objects")
+    if check and int(status.item()) != 0:
+        raise IndexError("yolo_loss_from_objects: a box centre or label lies outside the grid / class range")
+    return terms[4], grad, terms
+
+
 def scale_grad_(grad, grad_out):
     """grad *= grad_out (a 0-dim device tensor) in place; a no-op launch when grad_out == 1."""
     L = _lib.lib()
@@ -135,6 +177,24 @@ class _FusedYoloLoss(torch.autograd.Function):
         return scale_grad_(grad, grad_loss), None, None
 
 
+class _FusedYoloLossObjects(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, boxes, labels, offsets, cfg):
+        need = pred.requires_grad
+        loss, grad, terms = yolo_loss_from_objects(pred.detach(), boxes, labels, offsets, want_grad=need, **cfg)
+        ctx.grad = grad
+        ctx.mark_non_differentiable(terms)
+        return loss.clone(), terms
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_terms):
+        grad = ctx.grad
+        ctx.grad = None
+        if grad is None:
+            return None, None, None, None, None
+        return scale_grad_(grad, grad_loss), None, None, None, None
+
+
 class YOLOLossV1(nn.Module):
     """Drop-in for the reference `YOLOLossV1` (v1Loss.py:9-118): same constructor, same forward.
 
@@ -179,6 +239,16 @@ class YOLOLossV1(nn.Module):
             loss, terms = _FusedYoloLoss.apply(pred_tensor, target_tensor, self._cfg())
         else:
             loss, terms = self._forward_host(pred_tensor, target_tensor)
+        self.last_terms = terms
+        if self.logger or self.vis or self.verbose:
+            self._report(terms)
+        return loss
+
+    def forward_objects(self, pred_tensor, boxes, labels, offsets):
+        """forward(pred, encoder(boxes, labels)) without the dense target: the ragged object lists (CSR, see
+        `yolo_v1_b200.pack_objects`) go straight into the kernel.  Additive API; CUDA tensors only."""
+        cfg = self._cfg()
+        loss, terms = _FusedYoloLossObjects.apply(pred_tensor, boxes, labels, offsets, cfg)
         self.last_terms = terms
         if self.logger or self.vis or self.verbose:
             self._report(terms)
