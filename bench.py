@@ -414,10 +414,17 @@ def main():
     sm_mhz = clocks["sm_mhz"] or sm_max_mhz
     fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e12        # non-FMA fp32 lane-ops/s at the clock seen, Tops/s
     ach = NMS_OPS_PER_PAIR * pairs / (dms * 1e-3) / 1e12
+    insts = _traffic("decode_nms_kernel_warp_insts_per_launch")     # ncu smsp__inst_executed.sum of this very workload
+    issue_peak = 148 * 4 * sm_mhz * 1e6                             # warp instructions per second the SMs can issue
     dec["roofline"] = {"bound": "fp32-pipe (not a contraction: no tensor cores)", "achieved": ach, "peak": fp32_peak,
                        "unit": "Tops/s", "frac": ach / fp32_peak, "traffic": _traffic("decode_nms_kernel_bytes_per_launch"),
-                       "note": "13 fp32 ops per IoU pair x sum n(n-1)/2; small by construction -- the kernel is bound "
-                               "by shared-memory latency in the rank sort and the serial sweep, see DESIGN.md",
+                       "issue": None if not insts else {
+                           "warp_insts_per_launch": insts, "achieved_ginst_s": insts / (dms * 1e-3) / 1e9,
+                           "peak_ginst_s": issue_peak / 1e9, "frac": insts / (dms * 1e-3) / issue_peak,
+                           "note": "the kernel's real bound: instruction issue (148 SMs x 4 schedulers x clock)"},
+                       "note": "13 fp32 ops per IoU pair x sum n(n-1)/2; the fp32 fraction is small by construction -- "
+                               "the kernel is bound by instruction issue (compares, shared-memory traffic, the serial "
+                               "sweep), see DESIGN.md",
                        "hbm_gbs": (N_DEC * S_DEC * S_DEC * D * 4 + int(cnts.sum().item()) * 24) / (dms * 1e-3) / 1e9}
 
     # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------

@@ -17,7 +17,7 @@ from yolo_v1_b200 import synth
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, -1]   # launch shapes of the streaming kernel; -1 = strided kernel
+VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 13, -1]   # launch shapes of the streaming kernel; -1 = strided kernel
 
 
 def _y():
@@ -113,7 +113,7 @@ def test_planar_fast_path_all_shapes(S, N, dtype):
         pred = pred.to(torch.bfloat16)
     o_terms, o_grad = O.loss(pred.float().numpy(), target.numpy(), batch_size=N)
     planar = pred.cuda().permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
-    for variant in (0, 1):
+    for variant in (0, 1, 20, 21):
         _, grad, terms = y.yolo_loss_fused(planar, target.cuda(), batch_size=N, variant=variant)
         assert grad.stride() == planar.stride()
         if dtype == "f32":

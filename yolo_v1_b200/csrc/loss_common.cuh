@@ -73,6 +73,9 @@ struct CellSums {
 int launch_loss_nhwc(const LossParams& p, bool bf16, bool has_grad, int variant, cudaStream_t stream);
 int launch_loss_planar(const LossParams& p, bool bf16, bool has_grad, int tile_imgs, cudaStream_t stream);
 int planar_tile_imgs(int S, size_t esz, int target_cells, bool list_mode);
+// warp-specialised form (loss_ws.cu): tile_cells cells per tile, stages 2 or 3, gradient tile in place
+int launch_loss_ws(const LossParams& p, bool bf16, bool has_grad, bool is_planar, int tile_cells, int stages,
+                   cudaStream_t stream);
 
 namespace {
 

@@ -139,11 +139,7 @@ template <typename E, bool HAS_GRAD>
 int launch_tma_variant(const LossParams& p, int variant, cudaStream_t stream) {
   if (p.list_mode) {  // object-list targets
     if (p.logits) return launch_tma<E, HAS_GRAD, 128, 2, 2, true, true>(p, stream);
-    switch (variant) {
-      case 3: return launch_tma<E, HAS_GRAD, 64, 3, 2, false, true>(p, stream);
-      case 4: return launch_tma<E, HAS_GRAD, 64, 4, 3, false, true>(p, stream);
-      case 6: return launch_tma<E, HAS_GRAD, 32, 4, 2, false, true>(p, stream);
-      case 2: return launch_tma<E, HAS_GRAD, 128, 3, 2, false, true>(p, stream);
+    switch (variant) {  // other shapes measured slower
       default: return launch_tma<E, HAS_GRAD, 128, 2, 2, false, true>(p, stream);
     }
   }
@@ -158,10 +154,6 @@ int launch_tma_variant(const LossParams& p, int variant, cudaStream_t stream) {
     case 6: return launch_tma<E, HAS_GRAD, 32, 4, 2>(p, stream);
     case 7: return launch_tma<E, HAS_GRAD, 32, 6, 3>(p, stream);
     case 8: return launch_tma<E, HAS_GRAD, 128, 2, 0>(p, stream);   // in-place gradient tile: 61 KB, 3 CTAs/SM
-    case 9: return launch_tma<E, HAS_GRAD, 128, 3, 0>(p, stream);   // 92 KB, 2 CTAs/SM
-    case 10: return launch_tma<E, HAS_GRAD, 192, 2, 0>(p, stream);  // 92 KB, 2 CTAs/SM
-    case 11: return launch_tma<E, HAS_GRAD, 96, 2, 0>(p, stream);   // 46 KB, 4 CTAs/SM
-    case 12: return launch_tma<E, HAS_GRAD, 64, 2, 0>(p, stream);   // 31 KB, 7 CTAs/SM
     case 13: return launch_tma<E, HAS_GRAD, 256, 2, 0>(p, stream);  // 123 KB, 1 CTA/SM
     default: return YOLO1_ERR_ARG;
   }

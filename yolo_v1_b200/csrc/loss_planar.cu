@@ -142,22 +142,22 @@ int launch_planar_n(const LossParams& p, int tile_imgs, cudaStream_t stream) {
   return (int)cudaGetLastError();
 }
 
-// Two CTAs per SM are what keeps the copy engine busy (tools/tune_loss.py): separate output buffers while the
-// tile is small enough for that (<= 110 KB per CTA), gradient written in place over the pred stage otherwise.
+// This kernel (separate output buffers, two or more CTAs per SM) for small tiles; the warp-specialised kernel with the
+// gradient written in place over the pred stage (loss_ws.cu) for large ones.
 template <typename E, bool HAS_GRAD>
 int launch_planar(const LossParams& p, int tile_imgs, cudaStream_t stream) {
   const size_t tile_cells = (size_t)tile_imgs * p.S * p.S;
-  const size_t separate = 2 * tile_cells * 30 * (sizeof(E) + 4) + 2 * tile_cells * 30 * sizeof(E);
-  if (p.list_mode) {  // no dense target stage: two pred stages + two output buffers always fit twice per SM
+  const size_t separate = 2 * tile_cells * (30 * sizeof(E) + (p.list_mode ? 4 : 120)) + 2 * tile_cells * 30 * sizeof(E);
+  // measured (tools/tune_loss.py): whole-image tiles of a 14x14 grid (196 cells) run best warp-specialised with three
+  // in-place stages (fp32 0.753 ms vs 0.80, bf16 0.494 ms vs 0.537 at config-3 size); 98-cell tiles (S = 7) run best
+  // here with separate output buffers (0.717 ms vs 0.80)
+  if (separate > 110 * 1024 || tile_cells >= 160)
+    return launch_loss_ws(p, sizeof(E) == 2, HAS_GRAD, true, (int)tile_cells, 3, stream);
+  if (p.list_mode)
     return p.logits ? launch_planar_n<E, HAS_GRAD, 2, true, true>(p, tile_imgs, stream)
                     : launch_planar_n<E, HAS_GRAD, 2, false, true>(p, tile_imgs, stream);
-  }
-  if (p.logits) {
-    if (separate <= 110 * 1024) return launch_planar_n<E, HAS_GRAD, 2, true>(p, tile_imgs, stream);
-    return launch_planar_n<E, HAS_GRAD, 0, true>(p, tile_imgs, stream);
-  }
-  if (separate <= 110 * 1024) return launch_planar_n<E, HAS_GRAD, 2, false>(p, tile_imgs, stream);
-  return launch_planar_n<E, HAS_GRAD, 0, false>(p, tile_imgs, stream);
+  return p.logits ? launch_planar_n<E, HAS_GRAD, 2, true, false>(p, tile_imgs, stream)
+                  : launch_planar_n<E, HAS_GRAD, 2, false, false>(p, tile_imgs, stream);
 }
 
 }  // namespace
