@@ -427,6 +427,36 @@ def main():
                                "sweep), see DESIGN.md",
                        "hbm_gbs": (N_DEC * S_DEC * S_DEC * D * 4 + int(cnts.sum().item()) * 24) / (dms * 1e-3) / 1e9}
 
+    # ---------------- config 1 (the reference's own CPU-runnable case): latency of one small call --------------
+    sp, st_ = synth.make_loss_inputs(32, 7, seed=SEED + 1000, device=dev)
+    sg, sterms = torch.empty_like(sp), torch.empty(5, device=dev)
+
+    def small():
+        y.yolo_loss_fused(sp, st_, batch_size=32, out_grad=sg, out_terms=sterms, workspace=ws)
+
+    for _ in range(5):
+        small()
+    gr = torch.cuda.CUDAGraph()
+    cap = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(cap):
+        small()
+        cap.synchronize()
+        with torch.cuda.graph(gr, stream=cap):
+            small()
+    torch.cuda.synchronize()
+    c0, c1, c2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    c0.record()
+    for _ in range(200):
+        small()
+    c1.record()
+    for _ in range(200):
+        gr.replay()
+    c2.record()
+    torch.cuda.synchronize()
+    config1 = {"workload": "config1: loss fwd+bwd, N=32, S=7 (1568 cells), fits L2, launch-bound",
+               "us_per_call_eager": c0.elapsed_time(c1) / 200 * 1e3, "us_per_call_cuda_graph": c1.elapsed_time(c2) / 200 * 1e3,
+               "reference_python_ms_build_container": 176.0}
+
     # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -461,7 +491,7 @@ def main():
                    "parallelism": "batch-sharded x%d, one 20-byte NCCL all-reduce of the loss terms per step on a side stream" % world
                    if world > 1 else "single GPU", "timing": "CUDA events on the launch stream, max over ranks"},
         "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "decode_nms": dec, "parity": parity, "loss": loss_value,
+        "decode_nms": dec, "config1_latency": config1, "parity": parity, "loss": loss_value,
     }
     print(json.dumps(line), flush=True)
 

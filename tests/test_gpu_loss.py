@@ -345,3 +345,43 @@ def test_full_size_properties_config3():
     o_small, og_small = O.loss(pred[:64].cpu().numpy(), target[:64].cpu().numpy(), batch_size=N)
     assert np.abs(gr[:64].cpu().numpy() - og_small).max() <= TOL * np.abs(og_small).max()
     assert torch.equal(tr[1:4], terms[1:4])
+
+
+def test_cuda_graph_capture_and_replay():
+    """The C-ABI calls are stream ordered, allocation free and sync free, so a step (loss fwd+bwd, decode+NMS) can be
+    captured once into a CUDA graph and replayed -- what makes the launch-bound small-batch case (BASELINE config 1:
+    N=32, S=7) cheap."""
+    y = _y()
+    N, S = 32, 7
+    pred, target = synth.make_loss_inputs(N, S, seed=20241018, device="cuda")
+    grad, terms = torch.empty_like(pred), torch.empty(5, device="cuda")
+    ws = torch.empty(1 << 17, dtype=torch.uint8, device="cuda")
+    M = S * S * 2
+    outs = (torch.empty((N, M, 4), device="cuda"), torch.empty((N, M), dtype=torch.int32, device="cuda"),
+            torch.empty((N, M), device="cuda"), torch.empty((N,), dtype=torch.int32, device="cuda"))
+
+    def step():
+        y.yolo_loss_fused(pred, target, batch_size=N, out_grad=grad, out_terms=terms, workspace=ws)
+        y.decode_nms_batched(pred, 0.1, 0.5, out=outs)
+
+    step()
+    torch.cuda.synchronize()
+    want = (grad.clone(), terms.clone(), outs[0].clone(), outs[3].clone())
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        step()                       # warm-up on the capture stream
+        side.synchronize()
+        with torch.cuda.graph(g, stream=side):
+            step()
+    # new inputs, same buffers: the replay must see them
+    p2, t2 = synth.make_loss_inputs(N, S, seed=7, device="cuda")
+    pred.copy_(p2), target.copy_(t2)
+    g.replay()
+    torch.cuda.synchronize()
+    o_terms, o_grad = O.loss(p2.cpu().numpy(), t2.cpu().numpy(), batch_size=N)
+    _check(terms, grad, o_terms, o_grad, "graph replay")
+    assert not torch.equal(grad, want[0])
+    orc = O.decode_nms(p2.cpu().numpy(), thresh=0.1, nms_th=0.5)
+    assert np.array_equal(outs[3].cpu().numpy(), orc["counts"])
+    assert np.array_equal(outs[0].cpu().numpy().view(np.uint32), orc["boxes"].view(np.uint32))

@@ -18,6 +18,17 @@ int loss_launch_chunk(const void* pred, const int64_t ps[4], int pred_dtype, con
                       void* workspace, size_t workspace_bytes, int chunk_flags, int variant, cudaStream_t stream);
 }
 
+// Inside the chunk loops an error must not return straight away: copies and kernels of earlier chunks are still
+// in flight on the caller's buffers.  Record the code, leave the loop, and let the common exit drain the streams.
+#define HOST_TRY_BREAK(expr)          \
+  {                                   \
+    cudaError_t _e = (expr);          \
+    if (_e != cudaSuccess) {          \
+      rc = (int)_e;                   \
+      break;                          \
+    }                                 \
+  }
+
 namespace {
 constexpr int kBuf = 3;
 constexpr int kVariantHostMapped = 100;
@@ -186,16 +197,16 @@ int yolo1_loss_fwd_bwd_host(yolo1_host_ctx* c, const float* pred, const float* t
         for (int64_t k = 0; k < nchunks && rc == 0; ++k) {
           const int b = (int)(k % kBuf);
           const int64_t n0 = k * c->chunk, n = (N - n0 < c->chunk) ? N - n0 : c->chunk;
-          YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
-          YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_tgt[b], target + n0 * img, (size_t)n * img * 4, cudaMemcpyHostToDevice,
+          HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
+          HOST_TRY_BREAK(cudaMemcpyAsync(c->d_tgt[b], target + n0 * img, (size_t)n * img * 4, cudaMemcpyHostToDevice,
                                          c->s_in));
-          YOLO1_CUDA_TRY(cudaEventRecord(c->in_done[b], c->s_in));
-          YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
+          HOST_TRY_BREAK(cudaEventRecord(c->in_done[b], c->s_in));
+          HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
           const int flags = (k == 0 ? 1 : 0) | (k == nchunks - 1 ? 2 : 0);
           rc = yolo1::loss_launch_chunk(dp + n0 * img, st, YOLO1_DTYPE_F32, c->d_tgt[b], st, dg ? dg + n0 * img : nullptr,
                                         st, c->d_terms, n, S, c->B, c->C, lambda_coord, lambda_noobj, inv_batch_size,
                                         coord_mode, c->d_ws, c->ws_bytes, flags, kVariantHostMapped, c->s_k);
-          if (rc == 0) YOLO1_CUDA_TRY(cudaEventRecord(c->k_done[b], c->s_k));
+          if (rc == 0) HOST_TRY_BREAK(cudaEventRecord(c->k_done[b], c->s_k));
         }
       } else {  // zero_copy == 2: everything through the SMs, one launch
         rc = yolo1::loss_launch_chunk(dp, st, YOLO1_DTYPE_F32, dt, st, dg, st, c->d_terms, N, S, c->B, c->C,
@@ -229,29 +240,29 @@ int yolo1_loss_fwd_bwd_host(yolo1_host_ctx* c, const float* pred, const float* t
     const int64_t n0 = k * c->chunk, n = (N - n0 < c->chunk) ? N - n0 : c->chunk;
     const size_t bytes = (size_t)n * img * 4;
     // upload: the kernel that last read these staging buffers must be done
-    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
+    HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
     if (bytes) {
       if (!pred_alias)
-        YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_pred[b], pred + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
-      YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_tgt[b], target + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
+        HOST_TRY_BREAK(cudaMemcpyAsync(c->d_pred[b], pred + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
+      HOST_TRY_BREAK(cudaMemcpyAsync(c->d_tgt[b], target + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
     }
-    YOLO1_CUDA_TRY(cudaEventRecord(c->in_done[b], c->s_in));
+    HOST_TRY_BREAK(cudaEventRecord(c->in_done[b], c->s_in));
     // compute: inputs uploaded, previous download of this gradient buffer done
-    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
-    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->out_done[b], 0));
+    HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
+    HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_k, c->out_done[b], 0));
     const int flags = (k == 0 ? 1 : 0) | (k == nchunks - 1 ? 2 : 0);
     rc = yolo1::loss_launch_chunk(pred_alias ? pred_alias + n0 * img : c->d_pred[b], st, YOLO1_DTYPE_F32, c->d_tgt[b],
                                   st, grad ? c->d_grad[b] : nullptr, st, c->d_terms, n, S, c->B, c->C, lambda_coord,
                                   lambda_noobj, inv_batch_size, coord_mode, c->d_ws, c->ws_bytes, flags,
                                   pred_alias ? kVariantHostMapped : 0, c->s_k);
     if (rc) break;
-    YOLO1_CUDA_TRY(cudaEventRecord(c->k_done[b], c->s_k));
+    HOST_TRY_BREAK(cudaEventRecord(c->k_done[b], c->s_k));
     // download
     if (grad) {
-      YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->k_done[b], 0));
+      HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_out, c->k_done[b], 0));
       if (bytes)
-        YOLO1_CUDA_TRY(cudaMemcpyAsync(grad + n0 * img, c->d_grad[b], bytes, cudaMemcpyDeviceToHost, c->s_out));
-      YOLO1_CUDA_TRY(cudaEventRecord(c->out_done[b], c->s_out));
+        HOST_TRY_BREAK(cudaMemcpyAsync(grad + n0 * img, c->d_grad[b], bytes, cudaMemcpyDeviceToHost, c->s_out));
+      HOST_TRY_BREAK(cudaEventRecord(c->out_done[b], c->s_out));
     }
   }
   if (rc == 0) {
@@ -282,26 +293,26 @@ int yolo1_decode_nms_host(yolo1_host_ctx* c, const float* pred, int64_t N, doubl
   for (int64_t k = 0; k < nchunks; ++k) {
     const int b = (int)(k % kBuf);
     const int64_t n0 = k * c->chunk, n = (N - n0 < c->chunk) ? N - n0 : c->chunk;
-    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
-    YOLO1_CUDA_TRY(cudaMemcpyAsync(c->d_pred[b], pred + n0 * img, (size_t)n * img * 4, cudaMemcpyHostToDevice,
+    HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
+    HOST_TRY_BREAK(cudaMemcpyAsync(c->d_pred[b], pred + n0 * img, (size_t)n * img * 4, cudaMemcpyHostToDevice,
                                    c->s_in));
-    YOLO1_CUDA_TRY(cudaEventRecord(c->in_done[b], c->s_in));
-    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
-    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_k, c->out_done[b], 0));
+    HOST_TRY_BREAK(cudaEventRecord(c->in_done[b], c->s_in));
+    HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
+    HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_k, c->out_done[b], 0));
     rc = yolo1_decode_nms(c->d_pred[b], st, YOLO1_DTYPE_F32, n, S, c->B, c->C, thresh, iou_thr, per_class,
                           c->d_boxes[b], c->d_scores[b], c->d_cls[b], c->d_counts[b], nullptr, nullptr, c->s_k);
     if (rc) break;
-    YOLO1_CUDA_TRY(cudaEventRecord(c->k_done[b], c->s_k));
-    YOLO1_CUDA_TRY(cudaStreamWaitEvent(c->s_out, c->k_done[b], 0));
-    YOLO1_CUDA_TRY(cudaMemcpyAsync(out_boxes + n0 * M * 4, c->d_boxes[b], (size_t)n * M * 16,
+    HOST_TRY_BREAK(cudaEventRecord(c->k_done[b], c->s_k));
+    HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_out, c->k_done[b], 0));
+    HOST_TRY_BREAK(cudaMemcpyAsync(out_boxes + n0 * M * 4, c->d_boxes[b], (size_t)n * M * 16,
                                    cudaMemcpyDeviceToHost, c->s_out));
-    YOLO1_CUDA_TRY(cudaMemcpyAsync(out_scores + n0 * M, c->d_scores[b], (size_t)n * M * 4, cudaMemcpyDeviceToHost,
+    HOST_TRY_BREAK(cudaMemcpyAsync(out_scores + n0 * M, c->d_scores[b], (size_t)n * M * 4, cudaMemcpyDeviceToHost,
                                    c->s_out));
-    YOLO1_CUDA_TRY(cudaMemcpyAsync(out_cls + n0 * M, c->d_cls[b], (size_t)n * M * 4, cudaMemcpyDeviceToHost,
+    HOST_TRY_BREAK(cudaMemcpyAsync(out_cls + n0 * M, c->d_cls[b], (size_t)n * M * 4, cudaMemcpyDeviceToHost,
                                    c->s_out));
-    YOLO1_CUDA_TRY(cudaMemcpyAsync(out_counts + n0, c->d_counts[b], (size_t)n * 4, cudaMemcpyDeviceToHost,
+    HOST_TRY_BREAK(cudaMemcpyAsync(out_counts + n0, c->d_counts[b], (size_t)n * 4, cudaMemcpyDeviceToHost,
                                    c->s_out));
-    YOLO1_CUDA_TRY(cudaEventRecord(c->out_done[b], c->s_out));
+    HOST_TRY_BREAK(cudaEventRecord(c->out_done[b], c->s_out));
   }
   cudaError_t e1 = cudaStreamSynchronize(c->s_k), e2 = cudaStreamSynchronize(c->s_out),
               e3 = cudaStreamSynchronize(c->s_in);
