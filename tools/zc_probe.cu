@@ -50,6 +50,15 @@ int main() {
     CK(cudaEventElapsedTime(&ms, a, b));
     printf("memcpy D2H dense       : %.2f ms  %.1f GB/s\n", ms, bytes / ms / 1e6);
   }
+  {  // copy-engine gather: 8 bytes out of every 120-byte row (cudaMemcpy2DAsync, host pitch 120 -> device pitch 8)
+    for (int width = 8; width <= 32; width *= 2) {
+      CK(cudaMemcpy2DAsync(dp, width, hp, 120, width, cells, cudaMemcpyHostToDevice));
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(a)); CK(cudaMemcpy2DAsync(dp, width, hp, 120, width, cells, cudaMemcpyHostToDevice)); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+      CK(cudaEventElapsedTime(&ms, a, b));
+      printf("copy-engine 2D gather, %2d B of each 120-B row: %.2f ms  %.0f Mrows/s\n", width, ms, cells / ms / 1e3);
+    }
+  }
   for (int blocks_per_sm = 2; blocks_per_sm <= 8; blocks_per_sm *= 2) {
     for (int words = 1; words <= 2; ++words) {
       sparse_read<<<148 * blocks_per_sm, 256>>>(hp, ht, cells, words, out);

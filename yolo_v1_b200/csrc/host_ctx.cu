@@ -92,6 +92,19 @@ int ensure_decode_buffers(yolo1_host_ctx* c) {
   }
   return 0;
 }
+// Images per chunk for a call of N images: the context's chunk size is the maximum (its staging buffers), but a
+// batch that would fit one or two such chunks is cut finer (>= 8 chunks of >= ~2 MB) so that upload, kernel and
+// download still overlap -- a single chunk would run H2D, kernel and D2H back to back.
+int64_t call_chunk(const yolo1_host_ctx* c, int64_t N) {
+  const int64_t img_bytes = (int64_t)c->S * c->S * c->D * 4;
+  int64_t eff = (N + 7) / 8;
+  const int64_t floor_imgs = (2 << 20) / img_bytes > 0 ? (2 << 20) / img_bytes : 1;
+  if (eff < floor_imgs) eff = floor_imgs;
+  if ((img_bytes % 16) != 0 && (eff & 1)) eff += 1;   // keep chunk boundaries 16-byte aligned
+  if (eff > c->chunk) eff = c->chunk;
+  return eff;
+}
+
 int ensure_loss_buffers(yolo1_host_ctx* c) {
   if (c->d_tgt[0]) return 0;
   const size_t bytes = (size_t)c->chunk * c->S * c->S * c->D * 4;
@@ -156,7 +169,7 @@ void yolo1_host_ctx_destroy(yolo1_host_ctx* c) {
 
 int yolo1_host_ctx_set_zero_copy(yolo1_host_ctx* c, int enable) {
   if (!c) return YOLO1_ERR_ARG;
-  c->zero_copy = enable < 0 ? 0 : (enable > 3 ? 3 : enable);
+  c->zero_copy = enable < 0 ? 0 : (enable > 4 ? 4 : enable);
   return 0;
 }
 
@@ -178,6 +191,7 @@ int yolo1_loss_fwd_bwd_host(yolo1_host_ctx* c, const float* pred, const float* t
   const int S = c->S, D = c->D;
   const int64_t img = (int64_t)S * S * D;
   const int64_t st[4] = {img, (int64_t)S * D, D, 1};
+  const int64_t chunk = call_chunk(c, N);
   // Pinned + mapped buffers: one kernel reads the bytes it needs straight from host memory and stores the
   // gradient straight back (loss_hostmapped_kernel) -- no staging, far fewer bytes over PCIe.
   if ((c->zero_copy == 1 || c->zero_copy == 2) && c->B == 2 && c->C == 20 && N > 0 &&
@@ -193,10 +207,10 @@ int yolo1_loss_fwd_bwd_host(yolo1_host_ctx* c, const float* pred, const float* t
         // memory and bulk-store the gradient into the host buffer.  Chunks keep the `[:2]` carry (loss.cu).
         rc = ensure_loss_buffers(c);
         if (rc) return rc;
-        const int64_t nchunks = (N + c->chunk - 1) / c->chunk;
+        const int64_t nchunks = (N + chunk - 1) / chunk;
         for (int64_t k = 0; k < nchunks && rc == 0; ++k) {
           const int b = (int)(k % kBuf);
-          const int64_t n0 = k * c->chunk, n = (N - n0 < c->chunk) ? N - n0 : c->chunk;
+          const int64_t n0 = k * chunk, n = (N - n0 < chunk) ? N - n0 : chunk;
           HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
           HOST_TRY_BREAK(cudaMemcpyAsync(c->d_tgt[b], target + n0 * img, (size_t)n * img * 4, cudaMemcpyHostToDevice,
                                          c->s_in));
@@ -229,30 +243,37 @@ int yolo1_loss_fwd_bwd_host(yolo1_host_ctx* c, const float* pred, const float* t
   if (rc) return rc;
   // zero_copy == 3: only pred's confidences are pulled by the SMs from the caller's (pinned, mapped) buffer; the
   // dense target goes up and the gradient comes down through the copy engines as in the staged pipeline
+  // zero_copy == 4: pred AND target pulled sector-wise by the SMs, only the gradient goes through a copy engine
   const float* pred_alias = nullptr;
-  if (c->zero_copy == 3 && c->B == 2 && c->C == 20 && N > 0) {
+  const float* tgt_alias = nullptr;
+  if ((c->zero_copy == 3 || c->zero_copy == 4) && c->B == 2 && c->C == 20 && N > 0) {
     pred_alias = mapped_alias(pred);
     if ((uintptr_t)pred_alias % 16) pred_alias = nullptr;
+    if (pred_alias && c->zero_copy == 4) {
+      tgt_alias = mapped_alias(target);
+      if ((uintptr_t)tgt_alias % 16) tgt_alias = nullptr;
+    }
   }
-  const int64_t nchunks = N == 0 ? 1 : (N + c->chunk - 1) / c->chunk;
+  const int64_t nchunks = N == 0 ? 1 : (N + chunk - 1) / chunk;
   for (int64_t k = 0; k < nchunks; ++k) {
     const int b = (int)(k % kBuf);
-    const int64_t n0 = k * c->chunk, n = (N - n0 < c->chunk) ? N - n0 : c->chunk;
+    const int64_t n0 = k * chunk, n = (N - n0 < chunk) ? N - n0 : chunk;
     const size_t bytes = (size_t)n * img * 4;
     // upload: the kernel that last read these staging buffers must be done
     HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
     if (bytes) {
       if (!pred_alias)
         HOST_TRY_BREAK(cudaMemcpyAsync(c->d_pred[b], pred + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
-      HOST_TRY_BREAK(cudaMemcpyAsync(c->d_tgt[b], target + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
+      if (!tgt_alias)
+        HOST_TRY_BREAK(cudaMemcpyAsync(c->d_tgt[b], target + n0 * img, bytes, cudaMemcpyHostToDevice, c->s_in));
     }
     HOST_TRY_BREAK(cudaEventRecord(c->in_done[b], c->s_in));
     // compute: inputs uploaded, previous download of this gradient buffer done
     HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_k, c->in_done[b], 0));
     HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_k, c->out_done[b], 0));
     const int flags = (k == 0 ? 1 : 0) | (k == nchunks - 1 ? 2 : 0);
-    rc = yolo1::loss_launch_chunk(pred_alias ? pred_alias + n0 * img : c->d_pred[b], st, YOLO1_DTYPE_F32, c->d_tgt[b],
-                                  st, grad ? c->d_grad[b] : nullptr, st, c->d_terms, n, S, c->B, c->C, lambda_coord,
+    rc = yolo1::loss_launch_chunk(pred_alias ? pred_alias + n0 * img : c->d_pred[b], st, YOLO1_DTYPE_F32,
+                                  tgt_alias ? tgt_alias + n0 * img : c->d_tgt[b], st, grad ? c->d_grad[b] : nullptr, st, c->d_terms, n, S, c->B, c->C, lambda_coord,
                                   lambda_noobj, inv_batch_size, coord_mode, c->d_ws, c->ws_bytes, flags,
                                   pred_alias ? kVariantHostMapped : 0, c->s_k);
     if (rc) break;
@@ -289,10 +310,11 @@ int yolo1_decode_nms_host(yolo1_host_ctx* c, const float* pred, int64_t N, doubl
   const int S = c->S, D = c->D, M = c->max_n;
   const int64_t img = (int64_t)S * S * D;
   const int64_t st[4] = {img, (int64_t)S * D, D, 1};
-  const int64_t nchunks = (N + c->chunk - 1) / c->chunk;
+  const int64_t chunk = call_chunk(c, N);
+  const int64_t nchunks = (N + chunk - 1) / chunk;
   for (int64_t k = 0; k < nchunks; ++k) {
     const int b = (int)(k % kBuf);
-    const int64_t n0 = k * c->chunk, n = (N - n0 < c->chunk) ? N - n0 : c->chunk;
+    const int64_t n0 = k * chunk, n = (N - n0 < chunk) ? N - n0 : chunk;
     HOST_TRY_BREAK(cudaStreamWaitEvent(c->s_in, c->k_done[b], 0));
     HOST_TRY_BREAK(cudaMemcpyAsync(c->d_pred[b], pred + n0 * img, (size_t)n * img * 4, cudaMemcpyHostToDevice,
                                    c->s_in));
