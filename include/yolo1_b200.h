@@ -79,9 +79,10 @@ YOLO1_API int yolo1_loss_fwd_bwd(const void* pred, const int64_t pred_strides[4]
 
 /*
  * Tuning / diagnostic twin of yolo1_loss_fwd_bwd: `variant` picks the launch shape of the streaming kernel
- * (0 = the default yolo1_loss_fwd_bwd uses; 1..7 = other tile-cells x input-stages x output-buffers
- * shapes, see loss.cu launch_tma_variant; < 0 = force the strided one-thread-per-cell kernel that also
- * serves non-contiguous views).  Same results for every variant up to summation order.
+ * (0 = the default yolo1_loss_fwd_bwd uses; 1, 2, 3, 5, 8, 13 = other tile-cells x input-stages x output-buffers
+ * shapes, see loss_nhwc.cu launch_tma_variant; 20 = force the warp-specialised kernel for a channel-planar view;
+ * < 0 = force the strided one-thread-per-cell kernel that also serves non-contiguous views).  Same results for
+ * every variant up to summation order.
  */
 YOLO1_API int yolo1_loss_fwd_bwd_ex(const void* pred, const int64_t pred_strides[4], int pred_dtype,
                           const float* target, const int64_t target_strides[4],

@@ -17,7 +17,7 @@ from yolo_v1_b200 import synth
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7, 8, 13, -1]   # launch shapes of the streaming kernel; -1 = strided kernel
+VARIANTS = [0, 1, 2, 3, 5, 8, 13, -1]   # launch shapes of the streaming kernel; -1 = strided kernel
 
 
 def _y():
@@ -47,7 +47,7 @@ def test_golden_cases_from_the_reference(golden_dir):
         S, B, C, lc, ln, bs = z[name + "/hyper"]
         pred = torch.from_numpy(z[name + "/pred"]).cuda()
         target = torch.from_numpy(z[name + "/target"]).cuda()
-        for variant in (0, 6, -1):
+        for variant in (0, 3, -1):
             loss, grad, terms = y.yolo_loss_fused(pred, target, batch_size=float(bs), S=int(S), B=int(B), C=int(C),
                                                   l_coord=float(lc), l_noobj=float(ln), variant=variant)
             ref_loss, ref_grad = float(z[name + "/loss"]), z[name + "/grad"]
@@ -78,7 +78,7 @@ def test_ragged_sizes_and_tail_path(N):
     pred, target = synth.make_loss_inputs(N, 7, seed=5 + N, p_obj=0.2)
     bs = max(N, 1)
     o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=bs)
-    for variant in (0, 5, 6):
+    for variant in (0, 5, 3):
         _, grad, terms = y.yolo_loss_fused(pred.cuda(), target.cuda(), batch_size=bs, variant=variant)
         _check(terms, grad, o_terms, o_grad, ("ragged", N, variant))
 
@@ -113,7 +113,7 @@ def test_planar_fast_path_all_shapes(S, N, dtype):
         pred = pred.to(torch.bfloat16)
     o_terms, o_grad = O.loss(pred.float().numpy(), target.numpy(), batch_size=N)
     planar = pred.cuda().permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
-    for variant in (0, 1, 20, 21):
+    for variant in (0, 1, 20):
         _, grad, terms = y.yolo_loss_fused(planar, target.cuda(), batch_size=N, variant=variant)
         assert grad.stride() == planar.stride()
         if dtype == "f32":
@@ -152,7 +152,7 @@ def test_bf16_pred_and_grad():
     pred, target = synth.make_loss_inputs(40, 7, seed=11, p_obj=0.2)
     pb = pred.to(torch.bfloat16)
     o_terms, o_grad = O.loss(pb.float().numpy(), target.numpy(), batch_size=40)
-    for variant in (0, 6, -1):
+    for variant in (0, 3, -1):
         _, grad, terms = y.yolo_loss_fused(pb.cuda(), target.cuda(), batch_size=40, variant=variant)
         assert grad.dtype == torch.bfloat16
         _check(terms, None, o_terms, None, ("bf16", variant))

@@ -258,8 +258,8 @@ int loss_launch_chunk_impl(const void* pred, const int64_t ps[4], int pred_dtype
                            contiguous(ts, S, D) && (!grad || planar(gs, S, D)) && (uintptr_t)pred % 16 == 0 &&
                            (uintptr_t)target % 16 == 0 && (!grad || (uintptr_t)grad % 16 == 0);
   if (fast_planar) {
-    if (variant == 20 || variant == 21)
-      return launch_loss_ws(p, bf, grad != nullptr, true, tile_imgs * S * S, variant == 21 ? 3 : 2, stream);
+    if (variant == 20)  // force the warp-specialised kernel whatever the tile size
+      return launch_loss_ws(p, bf, grad != nullptr, true, tile_imgs * S * S, 3, stream);
     return launch_loss_planar(p, bf, grad != nullptr, tile_imgs, stream);
   }
   if (bf) return grad ? launch_generic<__nv_bfloat16, true>(p, stream) : launch_generic<__nv_bfloat16, false>(p, stream);

@@ -149,10 +149,7 @@ int launch_tma_variant(const LossParams& p, int variant, cudaStream_t stream) {
     case 1: return launch_tma<E, HAS_GRAD, 128, 2, 2>(p, stream);
     case 2: return launch_tma<E, HAS_GRAD, 128, 3, 2>(p, stream);
     case 3: return launch_tma<E, HAS_GRAD, 64, 3, 2>(p, stream);
-    case 4: return launch_tma<E, HAS_GRAD, 64, 4, 3>(p, stream);
     case 5: return launch_tma<E, HAS_GRAD, 256, 2, 2>(p, stream);
-    case 6: return launch_tma<E, HAS_GRAD, 32, 4, 2>(p, stream);
-    case 7: return launch_tma<E, HAS_GRAD, 32, 6, 3>(p, stream);
     case 8: return launch_tma<E, HAS_GRAD, 128, 2, 0>(p, stream);   // in-place gradient tile: 61 KB, 3 CTAs/SM
     case 13: return launch_tma<E, HAS_GRAD, 256, 2, 0>(p, stream);  // 123 KB, 1 CTA/SM
     default: return YOLO1_ERR_ARG;
