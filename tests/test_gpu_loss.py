@@ -385,3 +385,27 @@ def test_cuda_graph_capture_and_replay():
     orc = O.decode_nms(p2.cpu().numpy(), thresh=0.1, nms_th=0.5)
     assert np.array_equal(outs[3].cpu().numpy(), orc["counts"])
     assert np.array_equal(outs[0].cpu().numpy().view(np.uint32), orc["boxes"].view(np.uint32))
+
+
+def test_integration_md_ctypes_stub_runs_as_written():
+    """The binding INTEGRATION.md shows a maintainer of the reference (a ctypes stub against the C ABI) is executed
+    verbatim (only the library path is substituted) and must reproduce the oracle."""
+    import re
+    from yolo_v1_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", md, flags=re.S)
+    stub = [b for b in blocks if "class _Loss" in b]
+    assert len(stub) == 1
+    code = stub[0].replace('"libyolo1_b200.so"', repr(_lib.SO_PATH))
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    mod = ns["YOLOLossV1"]()
+    mod.S, mod.B, mod.C, mod.batch_size, mod.lambda_coord, mod.lambda_noobj = 7, 2, 20, 32, 5., .5
+    pred, target = synth.make_loss_inputs(32, 7, seed=20241018)
+    p = pred.cuda().requires_grad_(True)
+    loss = mod(p, target.cuda())
+    loss.backward()
+    o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=32)
+    assert abs(float(loss) - float(o_terms[4])) <= TOL * abs(float(o_terms[4]))
+    assert np.abs(p.grad.cpu().numpy() - o_grad).max() <= TOL * np.abs(o_grad).max()
