@@ -133,3 +133,19 @@ def test_loss_from_object_lists_equals_loss_on_encoded_target(layout, dtype, log
     with pytest.raises(IndexError):
         y.yolo_loss_from_objects(p.detach(), torch.tensor([[1.5, 0.5, 0.1, 0.1]]).cuda(), torch.tensor([0]).cuda(),
                                  torch.tensor([0, 1, 1, 1, 1]).cuda(), batch_size=4, check=True)
+
+
+@pytest.mark.gpu
+def test_loss_from_object_lists_empty_cases():
+    import yolo_v1_b200 as y
+    # no images at all
+    e = torch.zeros(0, 4).cuda(), torch.zeros(0, dtype=torch.int32).cuda()
+    _, g, t = y.yolo_loss_from_objects(torch.zeros(0, 7, 7, 30, device="cuda"), e[0], e[1],
+                                       torch.zeros(1, dtype=torch.int64).cuda(), batch_size=1)
+    assert g.numel() == 0 and float(t.abs().sum()) == 0
+    # images without any object: only the no-object confidence term remains
+    pred = torch.rand(5, 7, 7, 30, generator=torch.Generator().manual_seed(0)) * 0.98 + 0.01
+    _, g, t = y.yolo_loss_from_objects(pred.cuda(), e[0], e[1], torch.zeros(6, dtype=torch.int64).cuda(), batch_size=5)
+    o_terms, o_grad = O.loss(pred.numpy(), np.zeros((5, 7, 7, 30), np.float32), batch_size=5)
+    assert np.allclose(t.cpu().numpy(), o_terms, rtol=1e-5) and o_terms[0] == 0 and o_terms[3] == 0
+    assert np.abs(g.cpu().numpy() - o_grad).max() <= 1e-5 * np.abs(o_grad).max()
