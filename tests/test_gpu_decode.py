@@ -204,6 +204,15 @@ def test_host_buffer_path_equals_device_path():
         out = ctx.decode_nms(pred, 0.1, 0.5)
         got = (out["boxes"], out["cls"], out["scores"], out["counts"])
         _assert_batched_equal(got, orc, ("host", chunk))
+        # pinned input and outputs (full-rate copies), with either setting of the loss-only zero-copy switch
+        pp = pred.pin_memory()
+        for zc in (2, 0):
+            ctx.set_zero_copy(zc)
+            pin = dict(boxes=torch.full((300, 98, 4), -1.0).pin_memory(), scores=torch.full((300, 98), -1.0).pin_memory(),
+                       cls=torch.full((300, 98), -1, dtype=torch.int32).pin_memory(),
+                       counts=torch.full((300,), -1, dtype=torch.int32).pin_memory())
+            out = ctx.decode_nms(pp, 0.1, 0.5, out=pin)
+            _assert_batched_equal((out["boxes"], out["cls"], out["scores"], out["counts"]), orc, ("host pinned", chunk, zc))
         ctx.close()
 
 
