@@ -61,7 +61,7 @@ def test_cuda_encoder_bit_exact(golden_dir):
 def test_cuda_encoder_large_random_batches_vs_oracle_and_loss_consumes_it():
     import yolo_v1_b200 as y
     rng = np.random.RandomState(3)
-    for S, N in [(7, 4097), (14, 1025), (5, 33)]:
+    for S, N in [(7, 4097), (14, 1025), (5, 33), (7, 30001), (14, 6001)]:      # the last two: several tiles per CTA
         counts = rng.randint(0, 8, size=N)
         offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         boxes = rng.rand(int(offsets[-1]), 4).astype(np.float32)
