@@ -69,6 +69,10 @@ YOLO1_API size_t yolo1_loss_workspace_bytes(int64_t N, int S, int B, int C);
  * inv_batch_size : 1 / _batch_size of the constructor (v1Loss.py:18,105) -- NOT 1/N.
  * coord_mode : YOLO1_COORD_REFERENCE reproduces v1Loss.py:101 exactly.
  * The gradient includes the path through the IoU target (v1Loss.py:78 keeps the graph).
+ * grad must not overlap pred or target (the row-slice fix-up re-reads two cells of pred after the streaming pass).
+ * Fast paths: contiguous [N,S,S,30] tensors or the permuted NCHW view, B = 2, C = 20, 16-byte aligned bases; any
+ * other strides / alignment / (B, C) take the strided one-thread-per-cell kernel (same results, ~3x slower).
+ * N * S * S must be below 2^32 - 1 per call.
  */
 YOLO1_API int yolo1_loss_fwd_bwd(const void* pred, const int64_t pred_strides[4], int pred_dtype,
                        const float* target, const int64_t target_strides[4],
