@@ -1,5 +1,7 @@
+"""Development aid: the host-buffer loss call (yolo1_loss_fwd_bwd_host) in every transfer mode, with and without the
+gradient, config-3 size.  python tools/e2e_modes.py"""
 import sys, time, torch
-sys.path.insert(0, '/root/repo')
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import yolo_v1_b200 as y
 from yolo_v1_b200 import synth
 N, S = 65536, 14
