@@ -3,7 +3,8 @@ import pytest
 import torch
 
 from yolo_v1_b200 import synth
-from yolo_v1_b200.trainstep import LR_ADJUST_MAP, ResNet50Yolo, TrainStep, learning_rate_policy, warmming_up_policy
+from yolo_v1_b200.trainstep import (LR_ADJUST_MAP, DenseNet121Yolo, ResNet50Yolo, TrainStep, learning_rate_policy,
+                                    warmming_up_policy)
 
 
 def test_lr_policy_matches_train_py():
@@ -28,13 +29,19 @@ def test_head_shapes_and_strides():
     assert float(y.min()) >= 0 and float(y.max()) <= 1
     with pytest.raises(ValueError):
         ResNet50Yolo(9)
+    # the reference's default backbone (train.py:57): five dense blocks for S=7, four for S=14 (OriginDenseNet.py:159-161)
+    d7, d14 = DenseNet121Yolo(7), DenseNet121Yolo(14)
+    assert hasattr(d7.features, "denseblock5") and not hasattr(d14.features, "denseblock5")
+    with torch.no_grad():
+        z = d7.eval()(torch.randn(1, 3, 448, 448))
+    assert z.shape == (1, 7, 7, 30) and z.stride() == (1470, 7, 1, 49)
 
 
 @pytest.mark.gpu
 def test_one_bf16_train_step_updates_the_network():
     torch.manual_seed(0)
-    for fuse in (True, False):
-        ts = TrainStep(S=7, batch_size=4, device="cuda:0", fuse_head=fuse)
+    for fuse, backbone in ((True, "resnet50"), (False, "resnet50"), (True, "densenet121")):
+        ts = TrainStep(S=7, batch_size=4, device="cuda:0", fuse_head=fuse, backbone=backbone)
         ts.lr, ts.epoch = 0.0, 1          # epoch 1 -> lr 1e-3 (train.py:46-54)
         images = torch.randn(4, 3, 448, 448, device="cuda").to(memory_format=torch.channels_last)
         _, target = synth.make_loss_inputs(4, 7, seed=3, p_obj=0.1, device="cuda")

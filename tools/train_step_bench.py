@@ -23,12 +23,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--no-fuse-head", action="store_true")
+    ap.add_argument("--backbone", default="resnet50", choices=["resnet50", "densenet121"])
     a = ap.parse_args()
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    ts = TrainStep(S=a.S, batch_size=a.batch, device="cuda:%d" % lr, ddp=world > 1, fuse_head=not a.no_fuse_head)
+    ts = TrainStep(S=a.S, batch_size=a.batch, device="cuda:%d" % lr, ddp=world > 1, fuse_head=not a.no_fuse_head, backbone=a.backbone)
     images = torch.randn(a.batch, 3, 448, 448, device="cuda").to(memory_format=torch.channels_last)
     _, target = synth.make_loss_inputs(a.batch, a.S, seed=1 + rank, device="cuda")
     for _ in range(a.warmup):
@@ -60,8 +61,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(json.dumps({"config": "config5: ResNet50-YOLOv1 448x448 bf16 %s train step, S=%d, batch %d per GPU, fused loss%s" %
-                          ("DDP x%d" % world if world > 1 else "single GPU", a.S, a.batch, "" if a.no_fuse_head else " + fused sigmoid head"),
+        print(json.dumps({"config": "config5: %s-YOLOv1 448x448 bf16 %s train step, S=%d, batch %d per GPU, fused loss%s" %
+                          (a.backbone, "DDP x%d" % world if world > 1 else "single GPU", a.S, a.batch, "" if a.no_fuse_head else " + fused sigmoid head"),
                           "images_per_s": a.batch * world / (float(t) * 1e-3), "ms_per_step": float(t), "n_gpus": world,
                           "loss_fwd_bwd_ms": loss_ms, "loss_share_of_step": loss_ms / float(t), "loss": float(loss),
                           "pred_dtype": str(pred.dtype), "pred_strides": list(pred.stride())}))

@@ -12,7 +12,7 @@ import torch.nn as nn
 
 from .loss import YOLOLossV1
 
-__all__ = ["warmming_up_policy", "learning_rate_policy", "ResNet50Yolo", "TrainStep", "LR_ADJUST_MAP"]
+__all__ = ["warmming_up_policy", "learning_rate_policy", "ResNet50Yolo", "DenseNet121Yolo", "TrainStep", "LR_ADJUST_MAP"]
 
 LR_ADJUST_MAP = {1: 0.001, 75: 0.0001, 105: 0.00001}    # train.py:46-54 (epoch -> lr)
 
@@ -66,14 +66,39 @@ class ResNet50Yolo(nn.Module):
         return x.permute(0, 2, 3, 1)                         # :189 (a view; never made contiguous)
 
 
+class DenseNet121Yolo(nn.Module):
+    """OriginDenseNet.py:56-164 `densenet121(S=7|14)` (the reference's default backbone, train.py:57): torchvision
+    DenseNet-121 features with a fifth 16-layer dense block for S=7 (`block_config=(6,12,24,16,16)`, :159-161), ReLU,
+    1x1 conv 1024 -> 5B+C, BatchNorm, sigmoid, permute (:114-129)."""
+
+    def __init__(self, S=7, B=2, num_classes=20, return_logits=False):
+        super().__init__()
+        from torchvision.models.densenet import DenseNet
+        if S not in (7, 14):
+            raise ValueError("S must be 7 or 14")          # OriginDenseNet.py:155-157
+        cfg = (6, 12, 24, 16, 16) if S == 7 else (6, 12, 24, 16)
+        self.features = DenseNet(growth_rate=32, block_config=cfg, num_init_features=64).features
+        self.layer6 = nn.Conv2d(1024, B * 5 + num_classes, kernel_size=1, stride=1, bias=False)   # :100
+        self.bn_end = nn.BatchNorm2d(B * 5 + num_classes)                                         # :101
+        self.return_logits = return_logits
+
+    def forward(self, x):
+        x = torch.relu(self.features(x))
+        x = self.bn_end(self.layer6(x))
+        if not self.return_logits:
+            x = torch.sigmoid(x)                             # :127
+        return x.permute(0, 2, 3, 1)                         # :128
+
+
 class TrainStep:
     """One training iteration as train.py:155-172 runs it: lr policy, forward, loss, zero_grad, backward, step.
     bf16 autocast and DistributedDataParallel are the B200 additions (config 5)."""
 
     def __init__(self, S=7, B=2, C=20, batch_size=16, device="cuda", ddp=False, fuse_head=True, bf16=True,
-                 channels_last=True):
+                 channels_last=True, backbone="resnet50"):
         self.device = torch.device(device)
-        net = ResNet50Yolo(S, B, C, return_logits=fuse_head).to(self.device)
+        arch = {"resnet50": ResNet50Yolo, "densenet121": DenseNet121Yolo}[backbone]   # train.py:56-57
+        net = arch(S, B, C, return_logits=fuse_head).to(self.device)
         if channels_last:
             net = net.to(memory_format=torch.channels_last)
         self.net = nn.parallel.DistributedDataParallel(net, device_ids=[self.device.index]) if ddp else net
