@@ -136,13 +136,36 @@ def test_batch_size_divisor_lambdas_and_paper_mode():
         _check(terms, grad, o_terms, o_grad, (bs, lc, ln, mode))
 
 
-def test_general_B_and_C_use_the_strided_kernel():
+def test_general_B_and_C():
+    """Any (B <= 8, C): contiguous tensors go through the runtime-channel-count bulk-copy kernel (tile sized to the
+    channel count), other layouts through the strided kernel; both against the oracle."""
     y = _y()
-    for B, C in [(1, 20), (3, 5), (2, 21), (4, 1)]:
-        pred, target = synth.make_loss_inputs(12, 7, B=B, C=C, seed=B * 100 + C, p_obj=0.3, variant="mixed")
-        o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), B=B, C=C, batch_size=12)
-        _, grad, terms = y.yolo_loss_fused(pred.cuda(), target.cuda(), batch_size=12, B=B, C=C)
-        _check(terms, grad, o_terms, o_grad, (B, C))
+    for B, C, N in [(1, 20, 12), (3, 5, 12), (2, 21, 12), (4, 1, 12), (2, 80, 300), (8, 88, 40), (1, 1, 1000)]:
+        pred, target = synth.make_loss_inputs(N, 7, B=B, C=C, seed=B * 100 + C, p_obj=0.3, variant="mixed")
+        o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), B=B, C=C, batch_size=N)
+        for layout in ("nhwc", "strided"):
+            pc = pred.cuda()
+            if layout == "strided":
+                pc = torch.zeros(N, 7, 7, 5 * B + C + 2, device="cuda")[..., 1:1 + 5 * B + C].copy_(pred)
+            _, grad, terms = y.yolo_loss_fused(pc, target.cuda(), batch_size=N, B=B, C=C)
+            _check(terms, grad, o_terms, o_grad, (B, C, layout))
+            _, g0, t0 = y.yolo_loss_fused(pc, target.cuda(), batch_size=N, B=B, C=C, want_grad=False)
+            assert g0 is None and torch.allclose(t0, terms, rtol=2e-6, atol=1e-7)
+    # fused sigmoid head and bf16 with a non-default channel count
+    B, C, N = 2, 80, 64
+    _, target = synth.make_loss_inputs(N, 7, B=B, C=C, seed=5, p_obj=0.2)
+    z = torch.randn(N, 7, 7, 5 * B + C, generator=torch.Generator().manual_seed(2))
+    p64 = torch.sigmoid(z.double())
+    o_terms, o_grad = O.loss(p64.float().numpy(), target.numpy(), B=B, C=C, batch_size=N)
+    want = o_grad.astype(np.float64) * (p64 * (1 - p64)).numpy()
+    _, grad, terms = y.yolo_loss_fused(z.cuda(), target.cuda(), batch_size=N, B=B, C=C, from_logits=True)
+    assert np.all(np.abs(terms.cpu().numpy() - o_terms) <= 2e-5 * np.abs(o_terms) + 1e-7)
+    assert np.abs(grad.cpu().numpy() - want).max() <= 2e-5 * np.abs(want).max()
+    pb = torch.sigmoid(z).to(torch.bfloat16)
+    o_terms, o_grad = O.loss(pb.float().numpy(), target.numpy(), B=B, C=C, batch_size=N)
+    _, grad, terms = y.yolo_loss_fused(pb.cuda(), target.cuda(), batch_size=N, B=B, C=C)
+    _check(terms, None, o_terms, None, "bf16 C=80")
+    assert np.all(np.abs(grad.float().cpu().numpy() - o_grad) <= np.abs(o_grad) * 2.0 ** -8 + 1e-30)
 
 
 def test_bf16_pred_and_grad():

@@ -71,6 +71,7 @@ struct CellSums {
 
 // host-side launchers of the two streaming kernels (loss_nhwc.cu, loss_planar.cu); dispatch lives in loss.cu
 int launch_loss_nhwc(const LossParams& p, bool bf16, bool has_grad, int variant, cudaStream_t stream);
+int launch_loss_nhwc_any(const LossParams& p, bool bf16, bool has_grad, cudaStream_t stream);   // any (B, C)
 int launch_loss_planar(const LossParams& p, bool bf16, bool has_grad, int tile_imgs, cudaStream_t stream);
 int planar_tile_imgs(int S, size_t esz, int target_cells, bool list_mode);
 // warp-specialised form (loss_ws.cu): tile_cells cells per tile, stages 2 or 3, gradient tile in place
@@ -211,6 +212,26 @@ struct GlobOut {
   __device__ __forceinline__ void st(int c, float v) const {
     if (sig && v != 0.f) v *= dsigmoid_(ld_elem(z + c * zs));
     st_elem(p + c * cs, v);
+  }
+};
+// scalar view of a cell inside a shared-memory tile (runtime B, C; optional sigmoid head)
+template <typename E>
+struct SmemInS {
+  const E* p;
+  bool sig;
+  __device__ __forceinline__ float ld(int c) const {
+    const float v = ld_elem(p + c);
+    return sig ? sigmoid_(v) : v;
+  }
+};
+template <typename E>
+struct SmemOutS {
+  E* p;
+  const E* z;  // logits of the same cell (sig only)
+  bool sig;
+  __device__ __forceinline__ void st(int c, float v) const {
+    if (sig && v != 0.f) v *= dsigmoid_(ld_elem(z + c));
+    st_elem(p + c, v);
   }
 };
 // wrappers that put the sigmoid head in front of any pair accessor (shared-memory tiles)
@@ -395,7 +416,8 @@ __device__ __forceinline__ bool cell_b2c20(const PA& P, const TA& T, const GA& G
 // FIX = false: streaming pass (square-root / paper form).  FIX = true: finalize pass for one of the
 // call's first two object cells: writes only the 4 coordinate gradients of the responsible box in plain
 // form and returns (plain - sqrt) of the location sum in s.loc.
-template <bool HAS_GRAD, bool FIX, typename PA, typename TA, typename GA>
+// ZEROED = true: the gradient row was already cleared (cooperative vector stores), skip the zero stores.
+template <bool HAS_GRAD, bool FIX, bool ZEROED = false, typename PA, typename TA, typename GA>
 __device__ __forceinline__ bool cell_generic(const PA& P, const TA& T, const GA& G, const LossParams& k,
                                              CellSums& s) {
   const int B = k.B, C = k.C, D = 5 * B + C;
@@ -406,7 +428,7 @@ __device__ __forceinline__ bool cell_generic(const PA& P, const TA& T, const GA&
         s.miss += cf * cf;
         if (HAS_GRAD) G.st(b, k.k2ln * cf);
       }
-      if (HAS_GRAD)
+      if (HAS_GRAD && !ZEROED)
         for (int c = B; c < D; ++c) G.st(c, 0.f);
     }
     return false;
@@ -465,7 +487,7 @@ __device__ __forceinline__ bool cell_generic(const PA& P, const TA& T, const GA&
     if (HAS_GRAD) G.st(B + 4 * r + d, (k.lc * gl - 2.0f * dconf * dI[d]) * k.inv_bs);
   }
   s.loc += loc - loc_sqrt;
-  if (!FIX && HAS_GRAD)
+  if (!FIX && HAS_GRAD && !ZEROED)
     for (int b = 0; b < B; ++b)
       if (b != r)
         for (int d = 0; d < 4; ++d) G.st(B + 4 * b + d, 0.f);

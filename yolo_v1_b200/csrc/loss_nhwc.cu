@@ -156,7 +156,112 @@ int launch_tma_variant(const LossParams& p, int variant, cudaStream_t stream) {
   }
 }
 
+// ---- the same pipeline for any (B, C): contiguous [N,S,S,5B+C] tensors, runtime channel count -----------------
+// (other detectors' heads, e.g. 80 classes).  One thread per cell through cell_generic on scalar shared-memory
+// accessors; tile = blockDim cells, sized by the host so that two stages + two output buffers fit three times per SM.
+template <typename E, bool HAS_GRAD>
+__global__ void __launch_bounds__(128) loss_tma_any_kernel(const __grid_constant__ LossParams p) {
+  constexpr int STAGES = 2, NOUT = 2;
+  const int D = 5 * p.B + p.C, TILE = blockDim.x, tile_elems = TILE * D;
+  const uint32_t PB = tile_elems * sizeof(E), TB = tile_elems * sizeof(float), GB = PB;
+  extern __shared__ __align__(128) unsigned char smem[];
+  E* sp = reinterpret_cast<E*>(smem);
+  float* st = reinterpret_cast<float*>(smem + STAGES * PB);
+  E* so = reinterpret_cast<E*>(smem + STAGES * (PB + TB));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (PB + TB) + NOUT * GB);
+  const int tid = threadIdx.x;
+  const int64_t full = p.cells / TILE;
+  const int64_t my_n = full > (int64_t)blockIdx.x ? (full - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const E* gp = reinterpret_cast<const E*>(p.pred);
+  E* gg = reinterpret_cast<E*>(p.grad);
+  const bool sig = p.logits != 0;
+  uint64_t pol = 0;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+    mbar_fence_init();
+    pol = policy_evict_first();
+  }
+  __syncthreads();
+  auto issue = [&](int64_t k) {
+    const int s = (int)(k % STAGES);
+    const int64_t off = ((int64_t)blockIdx.x + k * gridDim.x) * tile_elems;
+    mbar_arrive_expect_tx(&bars[s], PB + TB);
+    bulk_g2s(sp + s * tile_elems, gp + off, PB, &bars[s], pol);
+    bulk_g2s(st + s * tile_elems, p.target + off, TB, &bars[s], pol);
+  };
+  if (tid == 0)
+    for (int64_t k = 0; k < my_n && k < STAGES; ++k) issue(k);
+  CellSums sums = {0.f, 0.f, 0.f, 0.f};
+  uint32_t m1 = 0, m2 = 0;
+  for (int64_t k = 0; k < my_n; ++k) {
+    const int s = (int)(k % STAGES), o = (int)(k % NOUT);
+    mbar_wait(&bars[s], (uint32_t)((k / STAGES) & 1));
+    if (HAS_GRAD) {
+      // most of the gradient tile is zero: clear it with 16-byte stores, the cells then write what is not
+      // (buffer o was released by the wait_group.read before the previous iteration's barrier)
+      uint4* z4 = reinterpret_cast<uint4*>(so + o * tile_elems);
+      for (int t = tid; t < (int)(GB / 16); t += TILE) z4[t] = make_uint4(0u, 0u, 0u, 0u);
+      __syncthreads();
+    }
+    const E* zc = sp + s * tile_elems + tid * D;
+    const SmemInS<E> P{zc, sig};
+    const SmemInS<float> T{st + s * tile_elems + tid * D, false};
+    const SmemOutS<E> G{so + o * tile_elems + tid * D, zc, sig};
+    if (cell_generic<HAS_GRAD, false, true>(P, T, G, p, sums))
+      note_object(m1, m2, ((int64_t)blockIdx.x + k * gridDim.x) * TILE + tid);
+    if (HAS_GRAD) {
+      fence_async_smem();
+      if (tid == 0) bulk_wait_read<NOUT - 2>();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (HAS_GRAD) {
+        bulk_s2g(gg + ((int64_t)blockIdx.x + k * gridDim.x) * tile_elems, so + o * tile_elems, GB, pol);
+        bulk_commit();
+      }
+      if (k + STAGES < my_n) issue(k + STAGES);
+    }
+  }
+  const int64_t tail0 = full * TILE;
+  if ((int64_t)blockIdx.x == full % gridDim.x && tail0 + tid < p.cells) {
+    const int64_t q = tail0 + tid;
+    const GlobIn<E> P{gp + q * D, 1, sig};
+    const GlobIn<float> T{p.target + q * D, 1, false};
+    const GlobOut<E> G{HAS_GRAD ? gg + q * D : nullptr, 1, gp + q * D, 1, sig};
+    if (cell_generic<HAS_GRAD, false>(P, T, G, p, sums)) note_object(m1, m2, q);
+  }
+  block_epilogue<E, HAS_GRAD, true>(sums, m1, m2, p);
+}
+
+template <typename E, bool HAS_GRAD>
+int launch_tma_any(const LossParams& p, cudaStream_t stream) {
+  const int D = 5 * p.B + p.C;
+  int tile = 128;
+  while (tile > 32 && (size_t)tile * D * (4 * sizeof(E) + 8) > 72 * 1024) tile >>= 1;   // 3 CTAs per SM
+  const size_t smem = (size_t)tile * D * (4 * sizeof(E) + 8) + 2 * sizeof(uint64_t);
+  if (smem > 200 * 1024) return YOLO1_ERR_UNSUPPORTED;
+  auto kern = loss_tma_any_kernel<E, HAS_GRAD>;
+  YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = kNumSMs, per_sm = 1;
+  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
+  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  YOLO1_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tile, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t tiles = p.cells / tile;
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > tiles) grid = tiles;
+  if (grid > kMaxGrid) grid = kMaxGrid;
+  if (grid < 1) grid = 1;
+  kern<<<(unsigned)grid, tile, smem, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace
+
+int launch_loss_nhwc_any(const LossParams& p, bool bf16, bool has_grad, cudaStream_t stream) {
+  if (bf16) return has_grad ? launch_tma_any<__nv_bfloat16, true>(p, stream) : launch_tma_any<__nv_bfloat16, false>(p, stream);
+  return has_grad ? launch_tma_any<float, true>(p, stream) : launch_tma_any<float, false>(p, stream);
+}
 
 int launch_loss_nhwc(const LossParams& p, bool bf16, bool has_grad, int variant, cudaStream_t stream) {
   if (bf16) return has_grad ? launch_tma_variant<__nv_bfloat16, true>(p, variant, stream)
