@@ -113,10 +113,7 @@ def test_strided_and_bf16_inputs():
     _assert_batched_equal(y.decode_nms_batched(planar, 0.1, 0.5, return_keep=True), orc, "planar")
     pb = pred.to(torch.bfloat16)
     orc_b = O.decode_nms(pb.float().numpy(), thresh=0.1, nms_th=0.5)
-    ties = synth.score_tie_images(pb.float())
-    got = y.decode_nms_batched(pb.cuda(), 0.1, 0.5)
-    ok = np.ones(64, bool)
-    ok[ties.numpy()] = False          # bf16 rounding can create score ties; tie order is canonical anyway
+    got = y.decode_nms_batched(pb.cuda(), 0.1, 0.5)    # bf16 rounding can create score ties: canonical order on both sides
     assert np.array_equal(got[3].cpu().numpy(), orc_b["counts"])
     assert np.array_equal(_bits(got[0].cpu().numpy()), _bits(orc_b["boxes"]))
 

@@ -196,9 +196,7 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float u, const DecodePa
 }
 
 __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodeParams& p) {
-  const float thr = p.iou_thr;
   const int per_class = p.per_class;
-  (void)thr;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int W = (n + 31) >> 5;
   // :161 order = scores descending; ties -> lower emission index first (canonical)

@@ -89,15 +89,15 @@ __global__ void __launch_bounds__(kGenericThreads) loss_generic_kernel(const __g
   uint32_t m1 = 0, m2 = 0;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < p.cells; q += stride) {
-    const E* zq = reinterpret_cast<const E*>(p.pred) + cell_offset<E>(p.ps, q, p.S);
+    const E* zq = reinterpret_cast<const E*>(p.pred) + cell_offset(p.ps, q, p.S);
     const GlobIn<E> P{zq, p.ps[3], p.logits != 0};
-    const GlobOut<E> G{HAS_GRAD ? reinterpret_cast<E*>(p.grad) + cell_offset<E>(p.gs, q, p.S) : nullptr, p.gs[3], zq,
+    const GlobOut<E> G{HAS_GRAD ? reinterpret_cast<E*>(p.grad) + cell_offset(p.gs, q, p.S) : nullptr, p.gs[3], zq,
                        p.ps[3], p.logits != 0};
     bool obj;
     if (p.list_mode) {
       obj = cell_generic<HAS_GRAD, false>(P, list_targetS(p, q), G, p, sums);
     } else {
-      const GlobIn<float> T{p.target + cell_offset<float>(p.ts, q, p.S), p.ts[3], false};
+      const GlobIn<float> T{p.target + cell_offset(p.ts, q, p.S), p.ts[3], false};
       obj = cell_generic<HAS_GRAD, false>(P, T, G, p, sums);
     }
     if (obj) note_object(m1, m2, q);

@@ -494,7 +494,6 @@ __device__ __forceinline__ bool cell_generic(const PA& P, const TA& T, const GA&
   return true;
 }
 
-template <typename E>
 __device__ __forceinline__ int64_t cell_offset(const int64_t st[4], int64_t q, int S) {
   const int64_t n = q / (S * S);
   const int rem = (int)(q - n * (S * S));
@@ -588,15 +587,15 @@ __device__ __noinline__ void block_epilogue(CellSums s, uint32_t m1, uint32_t m2
         if (seen < 2 && p.coord_mode == YOLO1_COORD_REFERENCE) {
           // v1Loss.py:101 `[:2]`: this object is one of the first two of the call -> plain form
           const int64_t q = (int64_t)(0xFFFFFFFFu - c[t]);
-          const E* zq = reinterpret_cast<const E*>(p.pred) + cell_offset<E>(p.ps, q, p.S);
+          const E* zq = reinterpret_cast<const E*>(p.pred) + cell_offset(p.ps, q, p.S);
           GlobIn<E> P{zq, p.ps[3], p.logits != 0};
-          GlobOut<E> G{HAS_GRAD ? reinterpret_cast<E*>(p.grad) + cell_offset<E>(p.gs, q, p.S) : nullptr, p.gs[3], zq,
+          GlobOut<E> G{HAS_GRAD ? reinterpret_cast<E*>(p.grad) + cell_offset(p.gs, q, p.S) : nullptr, p.gs[3], zq,
                        p.ps[3], p.logits != 0};
           CellSums d = {0.f, 0.f, 0.f, 0.f};
           if (p.list_mode) {
             cell_generic<HAS_GRAD, true>(P, list_targetS(p, q), G, p, d);
           } else {
-            GlobIn<float> T{p.target + cell_offset<float>(p.ts, q, p.S), p.ts[3], false};
+            GlobIn<float> T{p.target + cell_offset(p.ts, q, p.S), p.ts[3], false};
             cell_generic<HAS_GRAD, true>(P, T, G, p, d);
           }
           t4[0] += (double)d.loc;

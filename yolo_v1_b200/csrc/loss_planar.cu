@@ -104,14 +104,14 @@ __global__ void __launch_bounds__(256) loss_tma_planar_kernel(const __grid_const
   const int64_t tail0 = full * tile_cells;
   if ((int64_t)blockIdx.x == full % gridDim.x && tail0 + tid < p.cells && tid < tile_cells) {
     const int64_t q = tail0 + tid;
-    const E* zq = gp + cell_offset<E>(p.ps, q, p.S);
+    const E* zq = gp + cell_offset(p.ps, q, p.S);
     const GlobIn<E> P{zq, p.ps[3], SIG};
-    const GlobOut<E> G{HAS_GRAD ? gg + cell_offset<E>(p.gs, q, p.S) : nullptr, p.gs[3], zq, p.ps[3], SIG};
+    const GlobOut<E> G{HAS_GRAD ? gg + cell_offset(p.gs, q, p.S) : nullptr, p.gs[3], zq, p.ps[3], SIG};
     bool obj;
     if (LIST) {
       obj = cell_generic<HAS_GRAD, false>(P, list_targetS(p, q), G, p, sums);
     } else {
-      const GlobIn<float> T{p.target + cell_offset<float>(p.ts, q, p.S), p.ts[3], false};
+      const GlobIn<float> T{p.target + cell_offset(p.ts, q, p.S), p.ts[3], false};
       obj = cell_generic<HAS_GRAD, false>(P, T, G, p, sums);
     }
     if (obj) note_object(m1, m2, q);
