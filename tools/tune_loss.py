@@ -45,6 +45,25 @@ for name, p, g, variants in (("nhwc", pred, grad, [0, 5, 8, 13]), ("planar-view"
             print("%-12s variant %2d grad=%d  median %.3f ms  min %.3f ms  %.2f Gcells/s  %.0f GB/s (%.3f of measured %.0f)"
                   % (name, v, want_grad, med, ts[0], cells / med / 1e6, b / med / 1e6, b / med / 1e6 / peak, peak), flush=True)
 
+# ---- fused sigmoid head: pred holds logits ----
+logit = torch.logit(pred.float().clamp(1e-4, 1 - 1e-4)).to(pred.dtype)
+lplanar = logit.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+for name, p_, g_ in (("nhwc", logit, grad), ("planar-view", lplanar, gplanar)):
+    for _ in range(3):
+        y.yolo_loss_fused(p_, target, batch_size=N, out_grad=g_, out_terms=terms, workspace=ws, from_logits=True)
+    ts = []
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y.yolo_loss_fused(p_, target, batch_size=N, out_grad=g_, out_terms=terms, workspace=ws, from_logits=True)
+        e1.record()
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    b = cells * bytes_per_cell
+    print("%-12s fused sigmoid head   median %.3f ms  min %.3f ms  %.2f Gcells/s  %.0f GB/s (%.3f of measured)"
+          % (name, ts[5], ts[0], cells / ts[5] / 1e6, b / ts[5] / 1e6, b / ts[5] / 1e6 / peak), flush=True)
+
 # ---- loss from object lists (no dense target): 248 algorithmic bytes per cell (fp32) ----
 tgt_cells = (target[..., 0] == 1)
 cnt = tgt_cells.reshape(N, -1).sum(1)

@@ -151,17 +151,22 @@ struct SmemInBF16 {
     return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p + c));
   }
 };
+// writers: st2 stores a gradient pair; st2p additionally receives the two probabilities the caller already holds --
+// ignored here, used by the fused-head wrapper SigOut (d loss / d z = d loss / d p * p (1 - p)) so that no sigmoid
+// is evaluated twice
 struct SmemOutF32 {
   float* p;
   __device__ __forceinline__ void st2(int c, float x, float y) const {
     *reinterpret_cast<float2*>(p + c) = make_float2(x, y);
   }
+  __device__ __forceinline__ void st2p(int c, float x, float y, float, float) const { st2(c, x, y); }
 };
 struct SmemOutBF16 {
   __nv_bfloat16* p;
   __device__ __forceinline__ void st2(int c, float x, float y) const {
     *reinterpret_cast<__nv_bfloat162*>(p + c) = __floats2bfloat162_rn(x, y);
   }
+  __device__ __forceinline__ void st2p(int c, float x, float y, float, float) const { st2(c, x, y); }
 };
 template <typename E>
 struct SmemIn;
@@ -186,7 +191,15 @@ struct SmemOut<__nv_bfloat16> {
 
 // head epilogue fusion (backbones/OriginResNet.py:186-188: ... bn_end -> torch.sigmoid -> permute): p = sigmoid(z),
 // d loss / d z = d loss / d p * p (1 - p)
-__device__ __forceinline__ float sigmoid_(float z) { return 1.0f / (1.0f + expf(-z)); }
+// Branch-free: one MUFU.EX2 and one MUFU.RCP (~3 ulp).  The IEEE forms (expf, 1/x, __frcp_rn) carry a slow-path
+// branch each; 30 of them in a row on the one or two lanes of a warp that hold an object serialise into a
+// dependent chain the rest of the CTA waits for at the tile barrier (measured: 1.22 ms vs 0.72 ms without the head).
+__device__ __forceinline__ float sigmoid_(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
 __device__ __forceinline__ float dsigmoid_(float z) {
   const float pz = sigmoid_(z);
   return pz * (1.0f - pz);
@@ -243,16 +256,12 @@ struct SigIn {
     return make_float2(sigmoid_(v.x), sigmoid_(v.y));
   }
 };
-template <typename Out, typename In>
+template <typename Out>
 struct SigOut {
   Out out;
-  In z;  // the logits of the same cell; read before the (possibly aliasing) store
-  __device__ __forceinline__ void st2(int c, float x, float y) const {
-    if (x != 0.f || y != 0.f) {
-      const float2 v = z.ld2(c);
-      x *= dsigmoid_(v.x), y *= dsigmoid_(v.y);
-    }
-    out.st2(c, x, y);
+  __device__ __forceinline__ void st2(int c, float x, float y) const { out.st2(c, x, y); }   // zeros only
+  __device__ __forceinline__ void st2p(int c, float x, float y, float px, float py) const {
+    out.st2(c, x * (px * (1.0f - px)), y * (py * (1.0f - py)));
   }
 };
 
@@ -274,6 +283,7 @@ struct PlanarOut {
     st_elem(p + c * plane, x);
     st_elem(p + (c + 1) * plane, y);
   }
+  __device__ __forceinline__ void st2p(int c, float x, float y, float, float) const { st2(c, x, y); }
 };
 
 // ---- targets from object lists: what the reference encoder would have written into the cell ---------------
@@ -348,7 +358,7 @@ __device__ __forceinline__ bool cell_b2c20(const PA& P, const TA& T, const GA& G
     // v1Loss.py:91 -- both slots of a cell without object: conf^2 against the untouched 0 target
     s.miss += c01.x * c01.x + c01.y * c01.y;
     if (HAS_GRAD) {
-      G.st2(0, k.k2ln * c01.x, k.k2ln * c01.y);
+      G.st2p(0, k.k2ln * c01.x, k.k2ln * c01.y, c01.x, c01.y);
 #pragma unroll
       for (int c = 2; c < 30; c += 2) G.st2(c, 0.f, 0.f);
     }
@@ -375,7 +385,7 @@ __device__ __forceinline__ bool cell_b2c20(const PA& P, const TA& T, const GA& G
     const float2 pv = P.ld2(c), tv = T.ld2(c);
     const float dx = pv.x - tv.x, dy = pv.y - tv.y;
     cls += dx * dx + dy * dy;
-    if (HAS_GRAD) G.st2(c, k.k2 * dx, k.k2 * dy);
+    if (HAS_GRAD) G.st2p(c, k.k2 * dx, k.k2 * dy, pv.x, pv.y);
   }
   s.cls += cls;
   // confidences, v1Loss.py:90-91 (the IoU target is not detached: see the -2 dconf dIoU term below)
@@ -403,11 +413,11 @@ __device__ __forceinline__ bool cell_b2c20(const PA& P, const TA& T, const GA& G
 #pragma unroll
     for (int d = 0; d < 4; ++d) gv[d] = (k.lc * gl[d] - 2.0f * dconf * dI[d]) * k.inv_bs;
     const float g_r = k.k2 * dconf, g_o = k.k2ln * conf_o;
-    G.st2(0, r ? g_o : g_r, r ? g_r : g_o);
-    G.st2(2, r ? 0.f : gv[0], r ? 0.f : gv[1]);
-    G.st2(4, r ? 0.f : gv[2], r ? 0.f : gv[3]);
-    G.st2(6, r ? gv[0] : 0.f, r ? gv[1] : 0.f);
-    G.st2(8, r ? gv[2] : 0.f, r ? gv[3] : 0.f);
+    G.st2p(0, r ? g_o : g_r, r ? g_r : g_o, c01.x, c01.y);
+    G.st2p(2, r ? 0.f : gv[0], r ? 0.f : gv[1], p0[0], p0[1]);
+    G.st2p(4, r ? 0.f : gv[2], r ? 0.f : gv[3], p0[2], p0[3]);
+    G.st2p(6, r ? gv[0] : 0.f, r ? gv[1] : 0.f, p1[0], p1[1]);
+    G.st2p(8, r ? gv[2] : 0.f, r ? gv[3] : 0.f, p1[2], p1[3]);
   }
   return true;
 }

@@ -72,11 +72,11 @@ __global__ void __launch_bounds__(TILE) loss_tma_kernel(const __grid_constant__ 
         nxt = fetch_object(p, slots[tid]);
       }
       if (SIG)
-        obj = cell_b2c20<HAS_GRAD>(SigIn<PIn>{P}, TL, SigOut<GOut, PIn>{G, P}, p, sums);
+        obj = cell_b2c20<HAS_GRAD>(SigIn<PIn>{P}, TL, SigOut<GOut>{G}, p, sums);
       else
         obj = cell_b2c20<HAS_GRAD>(P, TL, G, p, sums);
     } else if (SIG) {
-      obj = cell_b2c20<HAS_GRAD>(SigIn<PIn>{P}, T, SigOut<GOut, PIn>{G, P}, p, sums);
+      obj = cell_b2c20<HAS_GRAD>(SigIn<PIn>{P}, T, SigOut<GOut>{G}, p, sums);
     } else {
       obj = cell_b2c20<HAS_GRAD>(P, T, G, p, sums);
     }

@@ -74,11 +74,11 @@ __global__ void __launch_bounds__(256) loss_tma_planar_kernel(const __grid_const
           nxt = fetch_object(p, slots[tid]);
         }
         if (SIG)
-          obj = cell_b2c20<HAS_GRAD>(SigIn<PlanarIn<E>>{P}, TL, SigOut<PlanarOut<E>, PlanarIn<E>>{G, P}, p, sums);
+          obj = cell_b2c20<HAS_GRAD>(SigIn<PlanarIn<E>>{P}, TL, SigOut<PlanarOut<E>>{G}, p, sums);
         else
           obj = cell_b2c20<HAS_GRAD>(P, TL, G, p, sums);
       } else if (SIG) {
-        obj = cell_b2c20<HAS_GRAD>(SigIn<PlanarIn<E>>{P}, T, SigOut<PlanarOut<E>, PlanarIn<E>>{G, P}, p, sums);
+        obj = cell_b2c20<HAS_GRAD>(SigIn<PlanarIn<E>>{P}, T, SigOut<PlanarOut<E>>{G}, p, sums);
       } else {
         obj = cell_b2c20<HAS_GRAD>(P, T, G, p, sums);
       }

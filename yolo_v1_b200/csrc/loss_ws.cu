@@ -97,13 +97,13 @@ __global__ void __launch_bounds__(288) loss_ws_kernel(const __grid_constant__ Lo
           const ListTarget2 TL = list_target2(p, nxt);
           if (k + 1 < my_n) nxt = fetch_object(p, reinterpret_cast<const int32_t*>(st + s * TB)[tid]);
           if (SIG)
-            obj = cell_b2c20<HAS_GRAD>(SigIn<PlanarIn<E>>{P}, TL, SigOut<PlanarOut<E>, PlanarIn<E>>{G, P}, p, sums);
+            obj = cell_b2c20<HAS_GRAD>(SigIn<PlanarIn<E>>{P}, TL, SigOut<PlanarOut<E>>{G}, p, sums);
           else
             obj = cell_b2c20<HAS_GRAD>(P, TL, G, p, sums);
         } else {
           const SmemInF32 T{reinterpret_cast<const float*>(st + s * TB) + tid * D};
           if (SIG)
-            obj = cell_b2c20<HAS_GRAD>(SigIn<PlanarIn<E>>{P}, T, SigOut<PlanarOut<E>, PlanarIn<E>>{G, P}, p, sums);
+            obj = cell_b2c20<HAS_GRAD>(SigIn<PlanarIn<E>>{P}, T, SigOut<PlanarOut<E>>{G}, p, sums);
           else
             obj = cell_b2c20<HAS_GRAD>(P, T, G, p, sums);
         }
