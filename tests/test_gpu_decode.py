@@ -180,6 +180,62 @@ def test_nms_semantics():
             assert np.array_equal(y.nms(b, s, thr).numpy(), O.nms(b.numpy(), s.numpy(), thr)), (n, thr)
 
 
+def test_nms_threshold_boundaries():
+    """`ovr <= threshold` (utils/utils.py:180) is evaluated without the division in the kernel (iou_exceeds): pairs
+    whose fp32 quotient is exactly the threshold, one ulp above and one ulp below must fall on the right side.
+    Expected values: the reference's op sequence in numpy float32 (IEEE division)."""
+    y = _y()
+    rng = np.random.default_rng(7)
+    n = 120000
+    a = rng.integers(2, 4096, n).astype(np.float32)
+    c = np.floor(rng.random(n) * a).astype(np.float32)              # 0 <= c < a: the two boxes overlap
+    b = rng.integers(1, 4096, n).astype(np.float32)
+    h = (rng.integers(1, 64, n) * 2.0 ** -6).astype(np.float32)
+    sc = np.float32(2.0 ** -12)
+    boxes = np.zeros((n, 2, 4), np.float32)
+    boxes[:, 0, 2], boxes[:, 0, 3] = a * sc, h
+    boxes[:, 1, 0], boxes[:, 1, 2], boxes[:, 1, 3] = c * sc, (c + b) * sc, h
+    scores = np.tile(np.array([0.9, 0.8], np.float32), (n, 1))
+    A, Bx = boxes[:, 0], boxes[:, 1]
+    area = lambda q: (q[:, 2] - q[:, 0]) * (q[:, 3] - q[:, 1])
+    w = np.maximum(np.minimum(Bx[:, 2], A[:, 2]) - np.maximum(Bx[:, 0], A[:, 0]), np.float32(0))
+    hh = np.maximum(np.minimum(Bx[:, 3], A[:, 3]) - np.maximum(Bx[:, 1], A[:, 1]), np.float32(0))
+    inter = w * hh
+    ovr = inter / ((area(A) + area(Bx)) - inter)
+    assert ovr.dtype == np.float32 and np.isfinite(ovr).all()
+    bd, sd = torch.from_numpy(boxes).cuda(), torch.from_numpy(scores).cuda()
+    counts = torch.full((n,), 2, dtype=torch.int32, device="cuda")
+    picks = ovr[rng.integers(0, n, 12)]
+    thrs = [0.5, 0.45, 0.25, float(np.float32(1) / np.float32(3)), 0.0, 1.0]
+    for v in picks:
+        thrs += [float(v), float(np.nextafter(v, np.float32(2))), float(np.nextafter(v, np.float32(-1)))]
+    ties = 0
+    for thr in thrs:
+        t32 = np.float32(thr)
+        want = np.where(ovr <= t32, 2, 1)
+        ties += int((ovr == t32).sum())
+        _, kc = y.nms_batched(bd, sd, counts, thr)
+        assert np.array_equal(kc.cpu().numpy(), want), thr
+    assert ties > 50   # the equality case is exercised
+
+
+def test_nms_nan_and_inf_boxes():
+    """NaN / infinite coordinates take the kernel's non-finite path; same keep lists as the oracle."""
+    y = _y()
+    g = torch.Generator().manual_seed(3)
+    for n in (2, 7, 40, 98):
+        xy = torch.rand(n, 2, generator=g) * 0.8
+        b = torch.cat([xy, xy + torch.rand(n, 2, generator=g) * 0.3 + 0.01], 1)
+        s = torch.randperm(n, generator=g).float() / n
+        for bad in (float("nan"), float("inf"), -float("inf"), 3.0e38):
+            bb = b.clone()
+            bb[n // 2, 2] = bad
+            bb[0, 1] = bad
+            if n > 7:
+                bb[5] = bad
+            assert np.array_equal(y.nms(bb, s, 0.5).numpy(), O.nms(bb.numpy(), s.numpy(), 0.5)), (n, bad)
+
+
 def test_helpers_match_reference_fixtures(golden_dir):
     import json
     y = _y()

@@ -9,8 +9,9 @@
 //   decode : max confidence (block reduce), per (cell, slot) candidate test, class arg-max, score,
 //            `double(score) > thresh`, order-preserving compaction (ballot + prefix) = emission order
 //   sort   : rank by counting (score descending, emission index ascending) -- deterministic, no ties left
-//   mask   : suppression bit-matrix; a warp takes a row i, lane <-> column j, __ballot_sync builds the word
-//            (dies iff !(IoU <= thr), utils/utils.py:180; the image tile is reused for the matrix)
+//   mask   : suppression bit-matrix; one thread per unordered pair (wrapped-diagonal enumeration, no idle lanes),
+//            the rare dead pair ORs its bit in (dies iff !(IoU <= thr), utils/utils.py:180; the image tile is
+//            reused for the matrix)
 //   sweep  : one warp walks the sorted boxes word by word; lane w holds word w of the removed-set; a kept
 //            box ORs its row in.  A suppressed box never suppresses (iterated semantics of the reference).
 //   store  : kept detections in descending score order (float4 boxes), counts.
@@ -32,9 +33,9 @@ struct DecodeParams {
   double thresh;  // python double, utils/utils.py:129
   float iou_thr;
   int per_class;
-  // division-free form of `fl32(inter / u) <= thr` (see set_threshold): thr_mid = midpoint between thr and the
-  // next float above it (exact in double); thr_tie_ok = 1 when that midpoint itself rounds down to thr
-  // (round-to-nearest-even); thr_fast = 0 when thr is outside the range where the shortcut is proven.
+  // division-free form of `fl32(inter / u) <= thr` (see set_threshold, iou_exceeds): thr_mid = midpoint between
+  // thr and the next float above it (exact in double), nudged up by two double ulps when that midpoint itself
+  // rounds down to thr (thr_tie_ok, round-to-nearest-even); thr_fast = 0 when thr is outside the proven range.
   double thr_mid;
   int thr_tie_ok;
   int thr_fast;
@@ -185,60 +186,110 @@ __device__ __forceinline__ int decode_phase(const DecodeParams& p, const Smem& s
 // ---- phase: rank sort + suppression matrix + sweep (utils/utils.py:150-184).  Returns kept count. --------
 // `!(fl32(inter / u) <= thr)` without the division.  fl32() is monotone, so fl32(x) <= thr  <=>  x < mid, or
 // x == mid when mid rounds to thr, where mid is the midpoint between thr and its successor.  For u > 0 that is
-// inter < mid * u; inter and u carry 24 significant bits and mid 25, so the product is exact in double.
-// Operands outside the proven range (u <= 0, non-finite, NaN, odd thresholds) take the real IEEE division.
+// inter < mid * u (or <=); inter and u carry 24 significant bits and mid 25, so the product is exact in double.
+// The `<=` case is folded into the constant: inter and mid * u are both multiples of 2^(e_mid + e_u - 47), so two
+// distinct values differ by more than 2^-49 relative; thr_mid = mid + 2 ulp_double (set_threshold) gives
+// fl64(thr_mid * u) in (mid u, mid u (1 + 2^-50)]: `<=` becomes `<` and no other case moves.
+// The test holds for every u > 0 including +inf (inter / inf = 0 survives; inf / u dies; NaN inter dies);
+// u <= 0 or NaN (0/0, negative areas) and thresholds outside the proven range take the real IEEE division.
 __device__ __forceinline__ bool iou_exceeds(float inter, float u, const DecodeParams& p) {
-  if (p.thr_fast && u > 0.f && u < 3.0e38f && inter >= 0.f && inter < 3.0e38f) {
-    const double lhs = (double)inter, rhs = p.thr_mid * (double)u;
-    return !(lhs < rhs || (p.thr_tie_ok && lhs == rhs));
-  }
+  if (p.thr_fast && u > 0.f) return !((double)inter < p.thr_mid * (double)u);
   return !(inter / u <= p.iou_thr);
 }
 
+// The suppression matrix.  Every unordered pair is visited exactly once: thread <-> row i, which it keeps in
+// registers, against the columns (i + d) mod n for the offsets d = 1 .. n/2 (for even n the last offset meets each
+// pair from both ends, so it runs over i < n/2 only).  Lanes are consecutive rows, so for a given d they read
+// consecutive boxes (conflict-free 128-bit loads).  When the CTA has room for several threads per row
+// (blockDim >= 2 n) the offsets are split between them.  The few pairs that die set their bit with a
+// shared-memory atomic OR; the earlier box of the pair (lower sorted position) plays the reference's box i.
+// FINITE = true: no coordinate of the image is NaN, so clamp(min=)/clamp(max=) are plain max/min (one FMNMX each)
+// and the intersection is symmetric in the two boxes.
+template <bool FINITE>
+__device__ __forceinline__ void nms_row(const Smem& sm, int n, int W, int i, int d0, int d1, const DecodeParams& p) {
+  const float4 A = sm.sbox[i];
+  const float area_i = sm.sarea[i];
+  int j = i + d0;
+  if (j >= n) j -= n;
+  for (int d = d0; d <= d1; ++d) {
+    const float4 Bx = sm.sbox[j];
+    const float area_j = (Bx.z - Bx.x) * (Bx.w - Bx.y);   // == sm.sarea[j], recomputed: cheaper than the load
+    float ww, hh;
+    if (FINITE) {
+      ww = fmaxf(fminf(Bx.z, A.z) - fmaxf(Bx.x, A.x), 0.f);
+      hh = fmaxf(fminf(Bx.w, A.w) - fmaxf(Bx.y, A.y), 0.f);
+    } else {
+      const bool fwd = i < j;   // box i is the earlier one
+      const float4 L = fwd ? A : Bx, R = fwd ? Bx : A;
+      const float xx1 = R.x < L.x ? L.x : R.x;  // clamp(min=x1[i])
+      const float yy1 = R.y < L.y ? L.y : R.y;
+      const float xx2 = R.z > L.z ? L.z : R.z;  // clamp(max=x2[i])
+      const float yy2 = R.w > L.w ? L.w : R.w;
+      ww = xx2 - xx1, hh = yy2 - yy1;
+      if (ww < 0.f) ww = 0.f;
+      if (hh < 0.f) hh = 0.f;
+    }
+    const float inter = ww * hh;
+    // ovr = inter / (a_i + a_j - inter)
+    if (iou_exceeds(inter, (area_i + area_j) - inter, p)) {
+      const int lo = min(i, j), hi = max(i, j);
+      if (!(p.per_class && sm.cls[sm.sidx[lo]] != sm.cls[sm.sidx[hi]]))
+        atomicOr(&sm.mask[lo * W + (hi >> 5)], 1u << (hi & 31));
+    }
+    if (++j == n) j = 0;
+  }
+}
+
+template <bool FINITE>
+__device__ __forceinline__ void nms_pairs(const Smem& sm, int n, int W, const DecodeParams& p) {
+  const int H = n >> 1;
+  const int G = max(1, (int)blockDim.x / n), K = (H + G - 1) / G;
+  for (int t = threadIdx.x; t < n * G; t += blockDim.x) {   // one round unless n > blockDim (then G == 1)
+    const int g = t / n, i = t - g * n;
+    const int d0 = g * K + 1;
+    int d1 = min(d0 + K - 1, H);
+    if (!(n & 1) && d1 == H && i >= H) --d1;
+    if (d0 > d1) continue;
+    nms_row<FINITE>(sm, n, W, i, d0, d1, p);
+  }
+}
+
 __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodeParams& p) {
-  const int per_class = p.per_class;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = (n + 31) >> 5;
-  // :161 order = scores descending; ties -> lower emission index first (canonical)
+  // the suppression matrix starts empty; dead pairs are rare and are OR-ed in below
+  for (int t = threadIdx.x; t < n * W; t += blockDim.x) sm.mask[t] = 0u;
+  // :161 order = scores descending; ties -> lower emission index first (canonical).
+  // Rank by counting, four scores per shared-memory load; equal scores are rare and resolved in a second loop.
+  bool nan = false;
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
     const float s = sm.score[k];
-    int rank = 0;
-    for (int m = 0; m < n; ++m) {
-      const float sm_ = sm.score[m];
-      rank += (sm_ > s) || (sm_ == s && m < k);
+    int rank = 0, eq = 0;
+    const int n4 = n & ~3;
+    for (int m = 0; m < n4; m += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(sm.score + m);
+      rank += (v.x > s) + (v.y > s) + (v.z > s) + (v.w > s);
+      eq += (v.x == s) + (v.y == s) + (v.z == s) + (v.w == s);
     }
+    for (int m = n4; m < n; ++m) {
+      const float v = sm.score[m];
+      rank += v > s;
+      eq += v == s;
+    }
+    if (eq > 1)
+      for (int m = 0; m < k; ++m) rank += sm.score[m] == s;
     const float4 b = sm.box[k];
+    nan |= !(b.x == b.x && b.y == b.y && b.z == b.z && b.w == b.w);
     sm.sbox[rank] = b;
     sm.sarea[rank] = (b.z - b.x) * (b.w - b.y);  // :159
     sm.sidx[rank] = k;
   }
-  __syncthreads();
-  // suppression matrix: row i, bit j (j > i) set iff box j dies when box i is kept (:166-180).
-  // A warp takes a row, then walks the words at or after the diagonal (columns before i are never consulted).
-  for (int i = warp; i < n; i += nwarps) {
-    const float4 A = sm.sbox[i];
-    const float area_i = sm.sarea[i];
-    const int cls_i = per_class ? sm.cls[sm.sidx[i]] : 0;
-    for (int w = i >> 5; w < W; ++w) {
-      const int j = (w << 5) + lane;
-      bool dead = false;
-      if (j > i && j < n) {
-        const float4 Bx = sm.sbox[j];
-        const float xx1 = Bx.x < A.x ? A.x : Bx.x;  // clamp(min=x1[i])
-        const float yy1 = Bx.y < A.y ? A.y : Bx.y;
-        const float xx2 = Bx.z > A.z ? A.z : Bx.z;  // clamp(max=x2[i])
-        const float yy2 = Bx.w > A.w ? A.w : Bx.w;
-        float ww = xx2 - xx1, hh = yy2 - yy1;
-        if (ww < 0.f) ww = 0.f;
-        if (hh < 0.f) hh = 0.f;
-        const float inter = ww * hh;
-        dead = iou_exceeds(inter, (area_i + sm.sarea[j]) - inter, p);   // ovr = inter / (a_i + a_j - inter)
-        if (per_class && cls_i != sm.cls[sm.sidx[j]]) dead = false;
-      }
-      const unsigned bits = __ballot_sync(0xffffffffu, dead);
-      if (lane == 0) sm.mask[i * W + w] = bits;
-    }
-  }
+  const int any_nan = __syncthreads_or(nan);
+  // suppression matrix: row i, bit j (j > i) set iff box j dies when box i is kept (:166-180)
+  if (any_nan)
+    nms_pairs<false>(sm, n, W, p);
+  else
+    nms_pairs<true>(sm, n, W, p);
   __syncthreads();
   // sweep: warp 0; lane w owns word w of the removed set (n <= 1024 -> W <= 32)
   if (warp == 0) {
@@ -388,6 +439,8 @@ void set_threshold(DecodeParams& p, float thr) {
     uint32_t bits;
     memcpy(&bits, &thr, 4);
     p.thr_tie_ok = (bits & 1u) == 0u;   // ties round to the even mantissa
+    // `x <= mid u` as `x < mid' u` with mid' two doubles above mid (see iou_exceeds)
+    if (p.thr_tie_ok) p.thr_mid = nextafter(nextafter(p.thr_mid, INFINITY), INFINITY);
   }
 }
 
