@@ -39,6 +39,7 @@ struct DecodeParams {
   double thr_mid;
   int thr_tie_ok;
   int thr_fast;
+  float thr_lo;   // fl32 just below thr (1 - 2^-20), 0 when !thr_fast: fp32 pre-test `inter < thr_lo * u` => survives
   // decode outputs / nms inputs
   float* boxes;
   float* scores;
@@ -58,10 +59,11 @@ struct DecodeParams {
 struct Smem {
   float* img;       // [S*S*D]   (decode)   -- aliased by mask after decode
   uint32_t* mask;   // [n * W]
-  float4* box;      // [max_n]  candidates in emission order
+  float4* box;      // [max_n]  candidates in emission order; dead after the sort, then the tail of sbox's wrap copy
   float* score;     // [max_n]
   int32_t* cls;     // [max_n]
-  float4* sbox;     // [max_n]  sorted by score
+  float4* sbox;     // [max_n]  sorted by score; after the sort sbox[n + r] = sbox[r] for r < n/2 (wrap-free reads),
+                    //          which runs over into `box`
   float* sarea;     // [max_n]
   int32_t* sidx;    // [max_n]  sorted position -> emission index
   int32_t* keep;    // [max_n]  kept sorted positions
@@ -78,9 +80,9 @@ __host__ __device__ inline size_t smem_layout(unsigned char* base, int img_float
   size_t off = 0;
   if (s) s->img = reinterpret_cast<float*>(base), s->mask = reinterpret_cast<uint32_t*>(base);
   off += align16(region);
-  if (s) s->box = reinterpret_cast<float4*>(base + off);
-  off += (size_t)max_n * 16;
   if (s) s->sbox = reinterpret_cast<float4*>(base + off);
+  off += (size_t)max_n * 16;
+  if (s) s->box = reinterpret_cast<float4*>(base + off);   // directly behind sbox: see the wrap copy in nms_phase
   off += (size_t)max_n * 16;
   if (s) s->score = reinterpret_cast<float*>(base + off);
   off += align16((size_t)max_n * 4);
@@ -203,23 +205,21 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float u, const DecodePa
 // consecutive boxes (conflict-free 128-bit loads).  When the CTA has room for several threads per row
 // (blockDim >= 2 n) the offsets are split between them.  The few pairs that die set their bit with a
 // shared-memory atomic OR; the earlier box of the pair (lower sorted position) plays the reference's box i.
-// FINITE = true: no coordinate of the image is NaN, so clamp(min=)/clamp(max=) are plain max/min (one FMNMX each)
-// and the intersection is symmetric in the two boxes.
+// FINITE = true: every coordinate of the image is an ordinary number (|c| < 1e18), so clamp(min=)/clamp(max=) are
+// plain max/min (one FMNMX each), the intersection is symmetric in the two boxes and nothing overflows.
 template <bool FINITE>
 __device__ __forceinline__ void nms_row(const Smem& sm, int n, int W, int i, int d0, int d1, const DecodeParams& p) {
   const float4 A = sm.sbox[i];
   const float area_i = sm.sarea[i];
-  int j = i + d0;
-  if (j >= n) j -= n;
-  for (int d = d0; d <= d1; ++d) {
-    const float4 Bx = sm.sbox[j];
+  for (int jj = i + d0; jj <= i + d1; ++jj) {   // jj may run past n: the sorted boxes are stored twice
+    const float4 Bx = sm.sbox[jj];
     const float area_j = (Bx.z - Bx.x) * (Bx.w - Bx.y);   // == sm.sarea[j], recomputed: cheaper than the load
     float ww, hh;
     if (FINITE) {
       ww = fmaxf(fminf(Bx.z, A.z) - fmaxf(Bx.x, A.x), 0.f);
       hh = fmaxf(fminf(Bx.w, A.w) - fmaxf(Bx.y, A.y), 0.f);
     } else {
-      const bool fwd = i < j;   // box i is the earlier one
+      const bool fwd = jj < n;   // box i is the earlier one
       const float4 L = fwd ? A : Bx, R = fwd ? Bx : A;
       const float xx1 = R.x < L.x ? L.x : R.x;  // clamp(min=x1[i])
       const float yy1 = R.y < L.y ? L.y : R.y;
@@ -230,13 +230,17 @@ __device__ __forceinline__ void nms_row(const Smem& sm, int n, int W, int i, int
       if (hh < 0.f) hh = 0.f;
     }
     const float inter = ww * hh;
-    // ovr = inter / (a_i + a_j - inter)
-    if (iou_exceeds(inter, (area_i + area_j) - inter, p)) {
+    const float u = (area_i + area_j) - inter;   // ovr = inter / (a_i + a_j - inter)
+    // FINITE: every coordinate is below 1e18 in magnitude, so inter and u are finite and not NaN.  fp32 pre-test:
+    // inter < fl32(thr_lo u) with a normal product implies inter / u < thr (thr_lo = thr (1 - 2^-20), one
+    // rounding of 2^-24), i.e. the pair survives -- the common case, settled without the exact test.
+    if (FINITE && fmaxf(inter, 1.17549435e-38f) < p.thr_lo * u) continue;
+    if (iou_exceeds(inter, u, p)) {
+      const int j = jj < n ? jj : jj - n;
       const int lo = min(i, j), hi = max(i, j);
       if (!(p.per_class && sm.cls[sm.sidx[lo]] != sm.cls[sm.sidx[hi]]))
         atomicOr(&sm.mask[lo * W + (hi >> 5)], 1u << (hi & 31));
     }
-    if (++j == n) j = 0;
   }
 }
 
@@ -261,7 +265,7 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
   for (int t = threadIdx.x; t < n * W; t += blockDim.x) sm.mask[t] = 0u;
   // :161 order = scores descending; ties -> lower emission index first (canonical).
   // Rank by counting, four scores per shared-memory load; equal scores are rare and resolved in a second loop.
-  bool nan = false;
+  bool wild = false;   // a NaN, infinite or huge coordinate: the image takes the general pair code
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
     const float s = sm.score[k];
     int rank = 0, eq = 0;
@@ -279,14 +283,17 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
     if (eq > 1)
       for (int m = 0; m < k; ++m) rank += sm.score[m] == s;
     const float4 b = sm.box[k];
-    nan |= !(b.x == b.x && b.y == b.y && b.z == b.z && b.w == b.w);
+    wild |= !(fabsf(b.x) < 1.0e18f && fabsf(b.y) < 1.0e18f && fabsf(b.z) < 1.0e18f && fabsf(b.w) < 1.0e18f);
     sm.sbox[rank] = b;
     sm.sarea[rank] = (b.z - b.x) * (b.w - b.y);  // :159
     sm.sidx[rank] = k;
   }
-  const int any_nan = __syncthreads_or(nan);
+  const int any_wild = __syncthreads_or(wild);
+  // wrap copy: row i reads the columns i+1 .. i+n/2 without a modulo.  It may run over into `box`, which is dead now.
+  for (int r = threadIdx.x; r < (n >> 1); r += blockDim.x) sm.sbox[n + r] = sm.sbox[r];
+  __syncthreads();
   // suppression matrix: row i, bit j (j > i) set iff box j dies when box i is kept (:166-180)
-  if (any_nan)
+  if (any_wild)
     nms_pairs<false>(sm, n, W, p);
   else
     nms_pairs<true>(sm, n, W, p);
@@ -432,7 +439,7 @@ int check_decode_args(const void* pred, const int64_t st[4], int dtype, int64_t 
 void set_threshold(DecodeParams& p, float thr) {
   p.iou_thr = thr;
   p.thr_fast = (thr >= 0.f && thr < 1.0e30f) ? 1 : 0;
-  p.thr_mid = 0.0, p.thr_tie_ok = 0;
+  p.thr_mid = 0.0, p.thr_tie_ok = 0, p.thr_lo = 0.f;
   if (p.thr_fast) {
     const float up = nextafterf(thr, INFINITY);
     p.thr_mid = 0.5 * ((double)thr + (double)up);
@@ -441,6 +448,7 @@ void set_threshold(DecodeParams& p, float thr) {
     p.thr_tie_ok = (bits & 1u) == 0u;   // ties round to the even mantissa
     // `x <= mid u` as `x < mid' u` with mid' two doubles above mid (see iou_exceeds)
     if (p.thr_tie_ok) p.thr_mid = nextafter(nextafter(p.thr_mid, INFINITY), INFINITY);
+    p.thr_lo = nextafterf((float)((double)thr * (1.0 - 0x1p-20)), 0.f);
   }
 }
 
