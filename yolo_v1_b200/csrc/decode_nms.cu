@@ -24,6 +24,7 @@ namespace yolo1 {
 namespace {
 
 constexpr int kMaxCand = 1024;
+constexpr int kRowAny = 64, kRankSum = 96;   // slots of Smem::misc (nms_phase)
 
 struct DecodeParams {
   const void* pred;
@@ -67,7 +68,7 @@ struct Smem {
   float* sarea;     // [max_n]
   int32_t* sidx;    // [max_n]  sorted position -> emission index
   int32_t* keep;    // [max_n]  kept sorted positions
-  int32_t* misc;    // [64]
+  int32_t* misc;    // [128]  0..63 decode scratch / kept count; 64..95 rows-with-bits words; 96 rank checksum
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -95,7 +96,7 @@ __host__ __device__ inline size_t smem_layout(unsigned char* base, int img_float
   if (s) s->keep = reinterpret_cast<int32_t*>(base + off);
   off += align16((size_t)max_n * 4);
   if (s) s->misc = reinterpret_cast<int32_t*>(base + off);
-  off += 64 * 4;
+  off += 128 * 4;
   return off;
 }
 
@@ -238,8 +239,10 @@ __device__ __forceinline__ void nms_row(const Smem& sm, int n, int W, int i, int
     if (iou_exceeds(inter, u, p)) {
       const int j = jj < n ? jj : jj - n;
       const int lo = min(i, j), hi = max(i, j);
-      if (!(p.per_class && sm.cls[sm.sidx[lo]] != sm.cls[sm.sidx[hi]]))
+      if (!(p.per_class && sm.cls[sm.sidx[lo]] != sm.cls[sm.sidx[hi]])) {
         atomicOr(&sm.mask[lo * W + (hi >> 5)], 1u << (hi & 31));
+        atomicOr(reinterpret_cast<unsigned*>(sm.misc) + kRowAny + (lo >> 5), 1u << (lo & 31));
+      }
     }
   }
 }
@@ -258,37 +261,57 @@ __device__ __forceinline__ void nms_pairs(const Smem& sm, int n, int W, const De
   }
 }
 
+// before the barrier that precedes nms_phase: clear what the phase accumulates into with atomics
+__device__ __forceinline__ void nms_prepare(const Smem& sm, int max_n) {
+  if (threadIdx.x < 33) sm.misc[kRowAny + threadIdx.x] = 0;   // 32 row words + the rank checksum
+  for (int t = threadIdx.x; t < max_n; t += blockDim.x) sm.sidx[t] = 0;   // NaN scores leave holes: keep them in range
+}
+
 __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodeParams& p) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = (n + 31) >> 5;
-  // the suppression matrix starts empty; dead pairs are rare and are OR-ed in below
+  // the suppression matrix starts empty; dead pairs are OR-ed in below
   for (int t = threadIdx.x; t < n * W; t += blockDim.x) sm.mask[t] = 0u;
   // :161 order = scores descending; ties -> lower emission index first (canonical).
-  // Rank by counting, four scores per shared-memory load; equal scores are rare and resolved in a second loop.
+  // Rank by counting the larger scores, four per shared-memory load.  Without equal scores the ranks are a
+  // permutation and add up to n (n - 1) / 2; a smaller sum means ties (rare): those images are ranked again with
+  // the tie rule.
   bool wild = false;   // a NaN, infinite or huge coordinate: the image takes the general pair code
+  int ranks = 0;
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
     const float s = sm.score[k];
-    int rank = 0, eq = 0;
+    int rank = 0;
     const int n4 = n & ~3;
     for (int m = 0; m < n4; m += 4) {
       const float4 v = *reinterpret_cast<const float4*>(sm.score + m);
       rank += (v.x > s) + (v.y > s) + (v.z > s) + (v.w > s);
-      eq += (v.x == s) + (v.y == s) + (v.z == s) + (v.w == s);
     }
-    for (int m = n4; m < n; ++m) {
-      const float v = sm.score[m];
-      rank += v > s;
-      eq += v == s;
-    }
-    if (eq > 1)
-      for (int m = 0; m < k; ++m) rank += sm.score[m] == s;
+    for (int m = n4; m < n; ++m) rank += sm.score[m] > s;
+    ranks += rank;
     const float4 b = sm.box[k];
     wild |= !(fabsf(b.x) < 1.0e18f && fabsf(b.y) < 1.0e18f && fabsf(b.z) < 1.0e18f && fabsf(b.w) < 1.0e18f);
     sm.sbox[rank] = b;
     sm.sarea[rank] = (b.z - b.x) * (b.w - b.y);  // :159
     sm.sidx[rank] = k;
   }
+  ranks = __reduce_add_sync(0xffffffffu, ranks);
+  if (lane == 0 && ranks) atomicAdd(&sm.misc[kRankSum], ranks);
   const int any_wild = __syncthreads_or(wild);
+  if (sm.misc[kRankSum] != n * (n - 1) / 2) {   // uniform: equal scores somewhere
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      const float s = sm.score[k];
+      int rank = 0;
+      for (int m = 0; m < n; ++m) {
+        const float v = sm.score[m];
+        rank += (v > s) || (v == s && m < k);
+      }
+      const float4 b = sm.box[k];
+      sm.sbox[rank] = b;
+      sm.sarea[rank] = (b.z - b.x) * (b.w - b.y);
+      sm.sidx[rank] = k;
+    }
+    __syncthreads();
+  }
   // wrap copy: row i reads the columns i+1 .. i+n/2 without a modulo.  It may run over into `box`, which is dead now.
   for (int r = threadIdx.x; r < (n >> 1); r += blockDim.x) sm.sbox[n + r] = sm.sbox[r];
   __syncthreads();
@@ -298,23 +321,25 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
   else
     nms_pairs<true>(sm, n, W, p);
   __syncthreads();
-  // sweep: warp 0; lane w owns word w of the removed set (n <= 1024 -> W <= 32)
+  // sweep: warp 0 walks the sorted boxes word by word; lane w owns word w of the removed set (n <= 1024 -> W <= 32).
+  // A kept box whose row is empty changes nothing, so only the live boxes with a non-empty row (misc[kRowAny]) are
+  // visited one after the other; what is left of `alive` at the end of a word are its kept boxes.
   if (warp == 0) {
     unsigned removed = 0;
     int kept = 0;
     for (int w = 0; w < W; ++w) {
       const unsigned valid = (w == W - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
       unsigned alive = ~__shfl_sync(0xffffffffu, removed, w) & valid;
-      while (alive) {
-        const int b = __ffs(alive) - 1;
-        const int i = (w << 5) + b;
-        if (lane == 0) sm.keep[kept] = i;
-        ++kept;
-        const unsigned row = (lane >= w && lane < W) ? sm.mask[i * W + lane] : 0u;
-        removed |= row;
-        alive &= ~__shfl_sync(0xffffffffu, row, w);
-        alive &= ~(1u << b);
+      unsigned todo = alive & (unsigned)sm.misc[kRowAny + w];
+      while (todo) {
+        const int b = __ffs(todo) - 1;
+        const unsigned* row = sm.mask + ((w << 5) + b) * W;
+        if (lane > w && lane < W) removed |= row[lane];
+        alive &= ~row[w];                   // bits above b only (j > i)
+        todo &= alive & (0xfffffffeu << b);  // drop b, what is before it and what just died
       }
+      if ((alive >> lane) & 1u) sm.keep[kept + __popc(alive & ((1u << lane) - 1u))] = (w << 5) + lane;
+      kept += __popc(alive);
     }
     if (lane == 0) sm.misc[0] = kept;
   }
@@ -330,6 +355,7 @@ __global__ void decode_nms_kernel(const __grid_constant__ DecodeParams p) {
   smem_layout(raw, p.S * p.S * (5 * p.B + p.C), p.max_n, &sm);
   const int64_t n = blockIdx.x;
   load_image<E>(p, n, sm.img);
+  nms_prepare(sm, p.max_n);
   __syncthreads();
   const int cand = decode_phase(p, sm);
   const int kept = cand > 0 ? nms_phase(sm, cand, p) : 0;
@@ -392,6 +418,7 @@ __global__ void nms_kernel(const __grid_constant__ DecodeParams p) {
     sm.score[t] = p.scores[src];
     sm.cls[t] = p.cls ? p.cls[src] : 0;
   }
+  nms_prepare(sm, p.max_n);
   __syncthreads();
   const int kept = cnt > 0 ? nms_phase(sm, cnt, p) : 0;
   for (int t = threadIdx.x; t < p.max_n; t += blockDim.x)
