@@ -106,8 +106,39 @@ __device__ __forceinline__ void load_image(const DecodeParams& p, int64_t n, flo
   const int S = p.S, D = 5 * p.B + p.C, total = S * S * D;
   const E* base = reinterpret_cast<const E*>(p.pred) + n * p.st[0];
   const bool dense = p.st[3] == 1 && p.st[2] == D && p.st[1] == (int64_t)S * D;
-  if (dense) {
-    for (int t = threadIdx.x; t < total; t += blockDim.x) img[t] = ld_elem(base + t);
+  if (dense && sizeof(E) == 4 && !(total & 1) && !((uintptr_t)base & 7)) {
+    // fp32, 8-byte aligned image: 64-bit loads, all of a thread's loads in flight before the first store
+    // (one trip to memory per CTA instead of one per unrolled group)
+    const float2* b2 = reinterpret_cast<const float2*>(base);
+    float2* i2 = reinterpret_cast<float2*>(img);
+    const int n2 = total >> 1;
+    for (int t0 = threadIdx.x; t0 < n2; t0 += 8 * blockDim.x) {
+      float2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + u * blockDim.x;
+        if (t < n2) v[u] = __ldg(b2 + t);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + u * blockDim.x;
+        if (t < n2) i2[t] = v[u];
+      }
+    }
+  } else if (dense) {
+    for (int t0 = threadIdx.x; t0 < total; t0 += 8 * blockDim.x) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + u * blockDim.x;
+        if (t < total) v[u] = ld_elem(base + t);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int t = t0 + u * blockDim.x;
+        if (t < total) img[t] = v[u];
+      }
+    }
   } else {
     for (int t = threadIdx.x; t < total; t += blockDim.x) {
       const int cell = t / D, c = t - cell * D;
@@ -208,42 +239,69 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float u, const DecodePa
 // shared-memory atomic OR; the earlier box of the pair (lower sorted position) plays the reference's box i.
 // FINITE = true: every coordinate of the image is an ordinary number (|c| < 1e18), so clamp(min=)/clamp(max=) are
 // plain max/min (one FMNMX each), the intersection is symmetric in the two boxes and nothing overflows.
+// intersection and union term of box A (area_a) with box Bx, by the reference's op sequence (:166-179)
+template <bool FINITE>
+__device__ __forceinline__ void pair_terms(const float4& A, float area_a, const float4& Bx, bool a_first, float& inter,
+                                           float& u) {
+  const float area_b = (Bx.z - Bx.x) * (Bx.w - Bx.y);   // == sm.sarea[j], recomputed: cheaper than the load
+  float ww, hh;
+  if (FINITE) {
+    ww = fmaxf(fminf(Bx.z, A.z) - fmaxf(Bx.x, A.x), 0.f);
+    hh = fmaxf(fminf(Bx.w, A.w) - fmaxf(Bx.y, A.y), 0.f);
+  } else {
+    const float4 L = a_first ? A : Bx, R = a_first ? Bx : A;   // L: the earlier box, the reference's box i
+    const float xx1 = R.x < L.x ? L.x : R.x;  // clamp(min=x1[i])
+    const float yy1 = R.y < L.y ? L.y : R.y;
+    const float xx2 = R.z > L.z ? L.z : R.z;  // clamp(max=x2[i])
+    const float yy2 = R.w > L.w ? L.w : R.w;
+    ww = xx2 - xx1, hh = yy2 - yy1;
+    if (ww < 0.f) ww = 0.f;
+    if (hh < 0.f) hh = 0.f;
+  }
+  inter = ww * hh;
+  u = (area_a + area_b) - inter;   // ovr = inter / (a_i + a_j - inter)
+}
+
+// the exact test of one pair; sets the matrix bit when the later box dies
+__device__ __forceinline__ void pair_settle(const Smem& sm, int n, int W, int i, int jj, float inter, float u,
+                                            const DecodeParams& p) {
+  if (!iou_exceeds(inter, u, p)) return;
+  const int j = jj < n ? jj : jj - n;
+  const int lo = min(i, j), hi = max(i, j);
+  if (p.per_class && sm.cls[sm.sidx[lo]] != sm.cls[sm.sidx[hi]]) return;
+  atomicOr(&sm.mask[lo * W + (hi >> 5)], 1u << (hi & 31));
+  atomicOr(reinterpret_cast<unsigned*>(sm.misc) + kRowAny + (lo >> 5), 1u << (lo & 31));
+}
+
+// FINITE: every coordinate is below 1e18 in magnitude, so inter and u are finite and not NaN.  fp32 pre-test:
+// inter < fl32(thr_lo u) with a normal product implies inter / u < thr (thr_lo = thr (1 - 2^-20), one rounding of
+// 2^-24), i.e. the pair survives -- the common case, settled without the exact test.
+template <bool FINITE>
+__device__ __forceinline__ bool pair_survives_fast(float inter, float u, float thr_lo) {
+  return FINITE && fmaxf(inter, 1.17549435e-38f) < thr_lo * u;
+}
+
 template <bool FINITE>
 __device__ __forceinline__ void nms_row(const Smem& sm, int n, int W, int i, int d0, int d1, const DecodeParams& p) {
   const float4 A = sm.sbox[i];
   const float area_i = sm.sarea[i];
-  for (int jj = i + d0; jj <= i + d1; ++jj) {   // jj may run past n: the sorted boxes are stored twice
-    const float4 Bx = sm.sbox[jj];
-    const float area_j = (Bx.z - Bx.x) * (Bx.w - Bx.y);   // == sm.sarea[j], recomputed: cheaper than the load
-    float ww, hh;
-    if (FINITE) {
-      ww = fmaxf(fminf(Bx.z, A.z) - fmaxf(Bx.x, A.x), 0.f);
-      hh = fmaxf(fminf(Bx.w, A.w) - fmaxf(Bx.y, A.y), 0.f);
-    } else {
-      const bool fwd = jj < n;   // box i is the earlier one
-      const float4 L = fwd ? A : Bx, R = fwd ? Bx : A;
-      const float xx1 = R.x < L.x ? L.x : R.x;  // clamp(min=x1[i])
-      const float yy1 = R.y < L.y ? L.y : R.y;
-      const float xx2 = R.z > L.z ? L.z : R.z;  // clamp(max=x2[i])
-      const float yy2 = R.w > L.w ? L.w : R.w;
-      ww = xx2 - xx1, hh = yy2 - yy1;
-      if (ww < 0.f) ww = 0.f;
-      if (hh < 0.f) hh = 0.f;
-    }
-    const float inter = ww * hh;
-    const float u = (area_i + area_j) - inter;   // ovr = inter / (a_i + a_j - inter)
-    // FINITE: every coordinate is below 1e18 in magnitude, so inter and u are finite and not NaN.  fp32 pre-test:
-    // inter < fl32(thr_lo u) with a normal product implies inter / u < thr (thr_lo = thr (1 - 2^-20), one
-    // rounding of 2^-24), i.e. the pair survives -- the common case, settled without the exact test.
-    if (FINITE && fmaxf(inter, 1.17549435e-38f) < p.thr_lo * u) continue;
-    if (iou_exceeds(inter, u, p)) {
-      const int j = jj < n ? jj : jj - n;
-      const int lo = min(i, j), hi = max(i, j);
-      if (!(p.per_class && sm.cls[sm.sidx[lo]] != sm.cls[sm.sidx[hi]])) {
-        atomicOr(&sm.mask[lo * W + (hi >> 5)], 1u << (hi & 31));
-        atomicOr(reinterpret_cast<unsigned*>(sm.misc) + kRowAny + (lo >> 5), 1u << (lo & 31));
-      }
-    }
+  const float thr_lo = p.thr_lo;
+  int jj = i + d0;   // jj may run past n: the head of the sorted boxes is repeated behind their end
+  const int jend = i + d1;
+  for (; jj < jend; jj += 2) {   // two columns per trip
+    const float4 B0 = sm.sbox[jj], B1 = sm.sbox[jj + 1];
+    float in0, u0, in1, u1;
+    pair_terms<FINITE>(A, area_i, B0, jj < n, in0, u0);
+    pair_terms<FINITE>(A, area_i, B1, jj + 1 < n, in1, u1);
+    const bool ok0 = pair_survives_fast<FINITE>(in0, u0, thr_lo), ok1 = pair_survives_fast<FINITE>(in1, u1, thr_lo);
+    if (ok0 && ok1) continue;
+    if (!ok0) pair_settle(sm, n, W, i, jj, in0, u0, p);
+    if (!ok1) pair_settle(sm, n, W, i, jj + 1, in1, u1, p);
+  }
+  if (jj == jend) {
+    float in0, u0;
+    pair_terms<FINITE>(A, area_i, sm.sbox[jj], jj < n, in0, u0);
+    if (!pair_survives_fast<FINITE>(in0, u0, thr_lo)) pair_settle(sm, n, W, i, jj, in0, u0, p);
   }
 }
 
