@@ -358,6 +358,65 @@ def main():
         ctx.close()
         del hg
 
+        # ---- the call as train.py:166-171 makes it: pred and its gradient live on the GPU (backbone output / input of
+        # the backbone's backward), the target arrives from the DataLoader in pinned host memory, the loss value goes
+        # back to the host for logging.  Two forms of the target: the reference's dense [N,S,S,30] tensor, and the
+        # object lists the DataLoader built it from (encoder inputs, utils/YOLODataLoader.py:200-230).
+        tdev = torch.empty_like(target)
+        hterm = torch.empty(5, dtype=torch.float32, pin_memory=True)
+        objmask = target[..., 0] == 1
+        idx = objmask.nonzero()
+        bx = target[idx[:, 0], idx[:, 1], idx[:, 2], 2:6]
+        cxcy = (bx[:, :2] + torch.stack([idx[:, 2], idx[:, 1]], 1).float()) / S_LOSS
+        offs = torch.zeros(N_LOSS + 1, dtype=torch.int64, device=dev)
+        offs[1:] = objmask.reshape(N_LOSS, -1).sum(1).cumsum(0)
+        h_boxes = torch.cat([cxcy, bx[:, 2:]], 1).contiguous().cpu().pin_memory()
+        h_labels = target[idx[:, 0], idx[:, 1], idx[:, 2], 10:].argmax(1).to(torch.int32).cpu().pin_memory()
+        h_offs = offs.cpu().pin_memory()
+        d_boxes, d_labels, d_offs = torch.empty_like(h_boxes, device=dev), torch.empty_like(h_labels, device=dev), offs
+        ws_obj = torch.empty(int(y._lib.lib().yolo1_loss_objects_workspace_bytes(N_LOSS, S_LOSS, B, C)),
+                             dtype=torch.uint8, device=dev)
+
+        def step_dense():
+            tdev.copy_(ht, non_blocking=True)
+            _, _, tt = y.yolo_loss_fused(pred, tdev, batch_size=N_LOSS, out_grad=grad, out_terms=terms, workspace=ws)
+            hterm.copy_(tt, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        def step_objects():
+            d_boxes.copy_(h_boxes, non_blocking=True)
+            d_labels.copy_(h_labels, non_blocking=True)
+            d_offs.copy_(h_offs, non_blocking=True)
+            _, _, tt = y.yolo_loss_from_objects(pred, d_boxes, d_labels, d_offs, batch_size=N_LOSS, out_grad=grad,
+                                                workspace=ws_obj)
+            hterm.copy_(tt, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        def time_host(fn, steps):
+            for _ in range(2):
+                fn()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+            el_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+            barrier()
+            assert abs(float(hterm[4]) - loss_value) <= 1e-5 * abs(loss_value)
+            return cells * world * steps / (el_ms * 1e-3), el_ms / steps
+
+        v_d, ms_d = time_host(step_dense, e2e_steps)
+        v_o, ms_o = time_host(step_objects, max(e2e_steps, 20))
+        e2e["train_step_call"] = {
+            "note": "supplementary (not the headline): the loss call where train.py:166-171 places it -- pred and grad "
+                    "stay on the GPU, the target comes from pinned host memory, the 5 loss terms go back to the host",
+            "dense_target": {"value": v_d, "unit": UNIT, "ms_per_step": ms_d, "h2d_bytes_per_step": nbytes,
+                             "d2h_bytes_per_step": 20},
+            "object_lists": {"value": v_o, "unit": UNIT, "ms_per_step": ms_o,
+                             "h2d_bytes_per_step": h_boxes.numel() * 4 + h_labels.numel() * 4 + h_offs.numel() * 8,
+                             "d2h_bytes_per_step": 20, "objects": int(h_labels.numel()),
+                             "api": "yolo1_loss_fwd_bwd_objects (targets as the encoder's inputs, never densified)"}}
+        del tdev
+
     # ---------------- decode + NMS (config 2) ----------------------------------------------------------
     dpred_h, redrawn = synth.make_tie_free_decode_inputs(N_DEC, S_DEC, seed=2)
     dpred = dpred_h.to(dev)
