@@ -10,7 +10,8 @@ import yolo_v1_b200 as y
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 7
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
 g = torch.Generator(device="cuda").manual_seed(1)
-counts = torch.randint(0, 7, (N,), generator=g, device="cuda")
+MAXC = int(sys.argv[3]) if len(sys.argv) > 3 else 7
+counts = torch.randint(0, MAXC, (N,), generator=g, device="cuda")
 offsets = torch.zeros(N + 1, dtype=torch.int64, device="cuda")
 offsets[1:] = counts.cumsum(0)
 n = int(offsets[-1])
