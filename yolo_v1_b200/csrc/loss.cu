@@ -107,29 +107,45 @@ __global__ void __launch_bounds__(kGenericThreads) loss_generic_kernel(const __g
 
 // object lists -> cell ownership map (yolo1_loss_fwd_bwd_objects): one thread per image walks its objects in input
 // order and records, per cell, the LAST object that falls into it (the reference encoder resets the cell before
-// each write, utils/YOLODataLoader.py:220).  cellobj was preset to -1.  4 bytes per cell instead of a 120-byte
+// each write, utils/YOLODataLoader.py:220); cells without object hold -1.  4 bytes per cell instead of a 120-byte
 // dense target row.
 __global__ void __launch_bounds__(256) object_cells_kernel(const float* __restrict__ boxes,
                                                            const int32_t* __restrict__ labels,
                                                            const int64_t* __restrict__ offsets, int64_t N, int S, int C,
-                                                           float cs, int32_t* __restrict__ cellobj,
+                                                           float cs, int G, int32_t* __restrict__ cellobj,
                                                            int32_t* __restrict__ status) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  for (int64_t k = offsets[n]; k < offsets[n + 1]; ++k) {
-    float fi, fj, d;
-    encode_axis(boxes[4 * k], cs, fi, d);
-    encode_axis(boxes[4 * k + 1], cs, fj, d);
-    int col = (int)fi, row = (int)fj;
-    const int lab = labels[k];
-    if (col < -S || col >= S || row < -S || row >= S || lab < -C || lab >= C) {  // reference: IndexError
-      atomicExch(status, 1);
-      continue;
+  // A CTA builds the map of G whole images in shared memory (all -1, then thread i walks image i's objects in input
+  // order) and writes it out with coalesced 16-byte stores: one launch, every map byte written once -- no memset of
+  // the map beforehand, no scattered 4-byte global stores.
+  extern __shared__ __align__(16) int32_t own[];
+  const int SS = S * S;
+  const int64_t g0 = (int64_t)blockIdx.x * G;
+  const int n_img = (int)((N - g0 < G) ? N - g0 : G);
+  const int total = n_img * SS;
+  for (int t = threadIdx.x; t < total; t += blockDim.x) own[t] = -1;
+  __syncthreads();
+  if ((int)threadIdx.x < n_img) {
+    const int64_t n = g0 + threadIdx.x;
+    for (int64_t k = offsets[n]; k < offsets[n + 1]; ++k) {
+      float fi, fj, d;
+      encode_axis(boxes[4 * k], cs, fi, d);
+      encode_axis(boxes[4 * k + 1], cs, fj, d);
+      int col = (int)fi, row = (int)fj;
+      const int lab = labels[k];
+      if (col < -S || col >= S || row < -S || row >= S || lab < -C || lab >= C) {  // reference: IndexError
+        atomicExch(status, 1);
+        continue;
+      }
+      if (col < 0) col += S;  // Python indexing
+      if (row < 0) row += S;
+      own[threadIdx.x * SS + row * S + col] = (int32_t)k;
     }
-    if (col < 0) col += S;  // Python indexing
-    if (row < 0) row += S;
-    cellobj[n * S * S + row * S + col] = (int32_t)k;
   }
+  __syncthreads();
+  int32_t* dst = cellobj + g0 * SS;   // 16-byte aligned: G * S * S is a multiple of 4 (host)
+  for (int t = threadIdx.x; t < (total >> 2); t += blockDim.x)
+    reinterpret_cast<int4*>(dst)[t] = reinterpret_cast<const int4*>(own)[t];
+  for (int t = (total & ~3) + threadIdx.x; t < total; t += blockDim.x) dst[t] = own[t];
 }
 
 // grad *= *scale (autograd's backward(grad_output)); returns untouched when the scalar is exactly 1
@@ -319,9 +335,13 @@ int yolo1_loss_fwd_bwd_objects_ex(const void* pred, const int64_t pred_strides[4
   const int64_t cells = N * S * S;
   YOLO1_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
   if (cells > 0) {
-    YOLO1_CUDA_TRY(cudaMemsetAsync(cellobj, 0xFF, (size_t)cells * sizeof(int32_t), s));  // -1: no object
-    object_cells_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(boxes, labels, offsets, N, S, C,
-                                                                    (float)(1.0 / (double)S), cellobj, status);
+    int G = 4096 / (S * S);   // ~16 KB of map per CTA
+    G = G < 4 ? 4 : (G > 256 ? 256 : (G & ~3));   // a multiple of 4 images keeps every CTA's slice 16-byte aligned
+    const size_t smem = (size_t)G * S * S * sizeof(int32_t);
+    if (smem > 200 * 1024) return YOLO1_ERR_UNSUPPORTED;
+    YOLO1_CUDA_TRY(cudaFuncSetAttribute(object_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    object_cells_kernel<<<(unsigned)((N + G - 1) / G), 256, smem, s>>>(boxes, labels, offsets, N, S, C,
+                                                                      (float)(1.0 / (double)S), G, cellobj, status);
     YOLO1_CUDA_TRY(cudaGetLastError());
   }
   const ObjectLists lists = {cellobj, boxes, labels};
