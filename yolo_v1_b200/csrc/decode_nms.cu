@@ -540,8 +540,9 @@ __global__ void __launch_bounds__(256) boxes_to_pixels_kernel(const float4* __re
   }
 }
 
-// measured (tools/tune_decode.py): 128 threads for a 7x7 grid (98 slots; 64: -17 %, 256: -5 %), 256-384 for 14x14
-int block_threads(int max_n) { return max_n <= 128 ? 128 : (max_n <= 256 ? 256 : 384); }
+// measured (profiles/tune_decode_r1.log): 96 threads for a 7x7 grid (98 slots: one row per thread in the pair loop,
+// three full warps; 128: -4 %, 160: -13 %, 256: -27 %), 384 for 14x14 (256: -3 %, 512: -3 %)
+int block_threads(int max_n) { return max_n <= 128 ? 96 : (max_n <= 256 ? 256 : 384); }
 
 template <typename K>
 int launch(K kern, const DecodeParams& p, int64_t N, int img_floats, cudaStream_t stream) {
