@@ -84,3 +84,32 @@ def test_decode_nms_fuzz():
         assert np.array_equal(got[0].cpu().numpy().view(np.uint32), orc["boxes"].view(np.uint32)), what
         assert np.array_equal(got[2].cpu().numpy().view(np.uint32), orc["scores"].view(np.uint32)), what
         assert np.array_equal(got[1].cpu().numpy(), orc["cls"]), what
+
+
+def test_nms_fuzz_with_ties_and_duplicates():
+    """Raw box sets through yolo1_nms: every size from tiny to past one CTA's thread count, heavily tied scores (the
+    rank-checksum path re-ranks those sets with the tie rule), duplicated boxes, class-aware and class-agnostic."""
+    import yolo_v1_b200 as y
+    rng = np.random.RandomState(11)
+    sizes = [1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65, 95, 96, 97, 98, 127, 128, 129, 255, 256, 257, 383, 384, 385, 392, 700]
+    for it, n in enumerate(sizes * 2):
+        xy = rng.rand(n, 2).astype(np.float32) * 0.7
+        wh = (rng.rand(n, 2) * 0.4 + 0.02).astype(np.float32)
+        b = np.concatenate([xy, xy + wh], 1)
+        if n > 3:
+            b[rng.randint(0, n, n // 4)] = b[rng.randint(0, n, n // 4)]        # exact duplicates (IoU = 1)
+        levels = int(rng.choice([1, 2, 5, 50, 10 ** 6]))
+        s = (rng.randint(0, levels, n) / float(levels)).astype(np.float32) + np.float32(0.01)
+        cls = rng.randint(0, 3, n).astype(np.int32)
+        thr = float(rng.choice([0.0, 0.3, 0.5, 0.75, 1.0]))
+        per_class = bool(it % 3 == 0)
+        M = n + int(rng.randint(0, 5))                                           # padded rows beyond the count
+        bb, ss, cc = np.zeros((1, M, 4), np.float32), np.zeros((1, M), np.float32), np.zeros((1, M), np.int32)
+        bb[0, :n], ss[0, :n], cc[0, :n] = b, s, cls
+        keep, kc = y.nms_batched(torch.from_numpy(bb).cuda(), torch.from_numpy(ss).cuda(),
+                                 torch.tensor([n], dtype=torch.int32), thr, cls=torch.from_numpy(cc).cuda(),
+                                 per_class=per_class)
+        want = O.nms(b, s, thr, cls=cls if per_class else None, per_class=per_class)
+        what = (it, n, levels, thr, per_class)
+        assert int(kc[0]) == len(want), what
+        assert np.array_equal(keep[0, :len(want)].cpu().numpy(), want), what
