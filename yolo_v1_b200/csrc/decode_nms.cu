@@ -40,7 +40,10 @@ struct DecodeParams {
   double thr_mid;
   int thr_tie_ok;
   int thr_fast;
-  float thr_lo;   // fl32 just below thr (1 - 2^-20), 0 when !thr_fast: fp32 pre-test `inter < thr_lo * u` => survives
+  // fp32 pre-test of the pair loop (pair_margin): thr_lo = thr (1 - 2^-18) rounded down, thr_k = 1 + thr_lo rounded up;
+  // thr_lo = 0 (nothing is ever settled by the pre-test) unless 2^-20 <= thr <= 4
+  float thr_lo, thr_k;
+  int s_magic;    // cell / S == (cell * s_magic) >> 16 for every cell of the grid (0: use the division)
   // decode outputs / nms inputs
   float* boxes;
   float* scores;
@@ -65,10 +68,11 @@ struct Smem {
   int32_t* cls;     // [max_n]
   float4* sbox;     // [max_n]  sorted by score; after the sort sbox[n + r] = sbox[r] for r < n/2 (wrap-free reads),
                     //          which runs over into `box`
-  float* sarea;     // [max_n]
+  float* sta;       // [max_n + max_n/2]  thr_lo * area of the sorted boxes, wrapped like sbox
   int32_t* sidx;    // [max_n]  sorted position -> emission index
   int32_t* keep;    // [max_n]  kept sorted positions
-  int32_t* misc;    // [128]  0..63 decode scratch / kept count; 64..95 rows-with-bits words; 96 rank checksum
+  int32_t* misc;    // [160]  0..63 decode scratch / kept count; 64..95 rows-with-bits words; 96 rank checksum;
+                    //        128..159 decode scratch
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -89,14 +93,14 @@ __host__ __device__ inline size_t smem_layout(unsigned char* base, int img_float
   off += align16((size_t)max_n * 4);
   if (s) s->cls = reinterpret_cast<int32_t*>(base + off);
   off += align16((size_t)max_n * 4);
-  if (s) s->sarea = reinterpret_cast<float*>(base + off);
-  off += align16((size_t)max_n * 4);
+  if (s) s->sta = reinterpret_cast<float*>(base + off);
+  off += align16((size_t)(max_n + max_n / 2) * 4);
   if (s) s->sidx = reinterpret_cast<int32_t*>(base + off);
   off += align16((size_t)max_n * 4);
   if (s) s->keep = reinterpret_cast<int32_t*>(base + off);
   off += align16((size_t)max_n * 4);
   if (s) s->misc = reinterpret_cast<int32_t*>(base + off);
-  off += 128 * 4;
+  off += 160 * 4;
   return off;
 }
 
@@ -148,73 +152,141 @@ __device__ __forceinline__ void load_image(const DecodeParams& p, int64_t n, flo
   }
 }
 
+// slot index t = cell * B + b, cell = i * S + j, without runtime divisions in the usual case (B = 2; s_magic)
+__device__ __forceinline__ void split_slot(const DecodeParams& p, int t, int& cell, int& b) {
+  cell = p.B == 2 ? (t >> 1) : t / p.B;
+  b = t - cell * p.B;
+}
+__device__ __forceinline__ void split_cell(const DecodeParams& p, int cell, int& i, int& j) {
+  i = p.s_magic ? (int)(((unsigned)cell * (unsigned)p.s_magic) >> 16) : cell / p.S;
+  j = cell - i * p.S;
+}
+
 // ---- phase: decode (utils/utils.py:108-132).  Returns the candidate count (uniform over the CTA). -----
-__device__ __forceinline__ int decode_phase(const DecodeParams& p, const Smem& sm) {
-  const int S = p.S, B = p.B, C = p.C, D = 5 * B + C, slots = S * S * B;
+struct SlotEval {   // what a slot carries across the barrier of its pass; the box is computed after it (slot_box)
+  float score;
+  int cls;
+  bool pass;
+};
+
+// One (cell, slot) of the image.  PAIRED (B == 2): the two slots of a cell sit in neighbouring lanes, so each lane
+// scans half of the class scores and the halves are merged with one shuffle (every lane of the warp must call).
+template <bool PAIRED>
+__device__ __forceinline__ SlotEval eval_slot(const DecodeParams& p, const Smem& sm, int t, int slots, float mx) {
+  const int B = p.B, C = p.C, D = 5 * B + C;
+  SlotEval r = {0.f, 0, false};
+  const bool live = t < slots;
+  int cell = 0, b = 0;
+  if (live) split_slot(p, t, cell, b);
+  const float* P = sm.img + cell * D;
+  float best_p;
+  int best_c;
+  if (PAIRED) {
+    // :127 first arg-max.  Lane b = 0 scans classes [0, C/2) starting from the first score like the reference's
+    // scan; lane b = 1 scans [C/2, C) from -inf (a later score only ever wins by `>`, so NaNs are passed over the
+    // same way); the upper half wins only if it is strictly larger.
+    const int half = (C + 1) >> 1, c0 = b ? half : 1, c1 = b ? C : half;
+    best_p = b ? -INFINITY : P[5 * B];
+    best_c = b ? half : 0;
+    for (int c = c0; c < c1; ++c) {
+      const float v = P[5 * B + c];
+      if (v > best_p) best_p = v, best_c = c;
+    }
+    const float op = __shfl_xor_sync(0xffffffffu, best_p, 1);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, 1);
+    const float lo_p = b ? op : best_p, hi_p = b ? best_p : op;
+    const int lo_c = b ? oc : best_c, hi_c = b ? best_c : oc;
+    best_p = hi_p > lo_p ? hi_p : lo_p;
+    best_c = hi_p > lo_p ? hi_c : lo_c;
+  } else {
+    best_p = P[5 * B], best_c = 0;
+    for (int c = 1; c < C; ++c) {
+      const float v = P[5 * B + c];
+      if (v > best_p) best_p = v, best_c = c;
+    }
+  }
+  const float conf = P[b];
+  if (live && (conf > 0.0001f || conf == mx)) {  // :108-114
+    r.score = conf * best_p;                      // :129
+    r.cls = best_c;
+    r.pass = (double)r.score > p.thresh;
+  }
+  return r;
+}
+
+// :119-126 the box of slot t, cell-relative xywh -> image xyxy
+__device__ __forceinline__ float4 slot_box(const DecodeParams& p, const Smem& sm, int t) {
+  int cell, b, i, j;
+  split_slot(p, t, cell, b);
+  split_cell(p, cell, i, j);
+  const float* Q = sm.img + cell * (5 * p.B + p.C) + p.B + 4 * b;
+  const float x = Q[0], y = Q[1], w = Q[2], h = Q[3];
+  const float cx = x * p.cs + (float)j * p.cs;  // :122-123 (no FMA: file is built with -fmad=false)
+  const float cy = y * p.cs + (float)i * p.cs;
+  const float hw = 0.5f * w, hh = 0.5f * h;
+  return make_float4(cx - hw, cy - hh, cx + hw, cy + hh);
+}
+
+template <bool PAIRED, bool TWO>
+__device__ __forceinline__ int decode_phase_impl(const DecodeParams& p, const Smem& sm) {
+  const int S = p.S, B = p.B, D = 5 * B + p.C, slots = S * S * B;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-  float* red = reinterpret_cast<float*>(sm.misc);  // [32] floats, then [32] ints
-  int* wcount = sm.misc + 32;
+  float* red = reinterpret_cast<float*>(sm.misc);  // [32] floats
+  int* wcount = sm.misc + 32;                      // [32] ints: first round of a pass; wcount2: second round
+  int* wcount2 = sm.misc + 128;
   // :109-113 max over the confidences of the image
   float mx = -INFINITY;
   for (int t = threadIdx.x; t < slots; t += blockDim.x) {
-    const int cell = t / B, b = t - cell * B;
+    int cell, b;
+    split_slot(p, t, cell, b);
     mx = fmaxf(mx, sm.img[cell * D + b]);
   }
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
   __syncthreads();
-  mx = red[0];
-  for (int w = 1; w < nwarps; ++w) mx = fmaxf(mx, red[w]);
-  __syncthreads();
+  mx = warp_max(lane < nwarps ? red[lane] : -INFINITY);
 
-  int base = 0;  // candidates emitted by earlier rounds (uniform)
-  for (int t0 = 0; t0 < slots; t0 += blockDim.x) {
-    const int t = t0 + threadIdx.x;
-    bool pass = false;
-    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
-    float score = 0.f;
-    int best_c = 0;
-    if (t < slots) {
-      const int cell = t / B, b = t - cell * B;
-      const int i = cell / S, j = cell - i * S;
-      const float* P = sm.img + cell * D;
-      const float conf = P[b];
-      if (conf > 0.0001f || conf == mx) {  // :108-114
-        float best_p = P[5 * B];
-        for (int c = 1; c < C; ++c) {      // :127 first arg-max
-          const float v = P[5 * B + c];
-          if (v > best_p) best_p = v, best_c = c;
-        }
-        score = conf * best_p;             // :129
-        if ((double)score > p.thresh) {
-          pass = true;
-          const float x = P[B + 4 * b], y = P[B + 4 * b + 1], w = P[B + 4 * b + 2], h = P[B + 4 * b + 3];
-          const float cx = x * p.cs + (float)j * p.cs;  // :122-123 (no FMA: file is built with -fmad=false)
-          const float cy = y * p.cs + (float)i * p.cs;
-          const float hw = 0.5f * w, hh = 0.5f * h;
-          bx = make_float4(cx - hw, cy - hh, cx + hw, cy + hh);  // :124-126
-        }
+  // TWO: two rounds of slots per pass (slot t and slot t + blockDim).  With 98 slots on 96 threads the second round
+  // is two slots in the first warp, and one pass means one barrier pair and one prefix.  (Not for the large-grid
+  // kernel: carrying the second slot across the barrier costs it 4 registers and with them a resident CTA.)
+  int base = 0;  // candidates emitted by earlier passes (uniform)
+  for (int t0 = 0; t0 < slots; t0 += (TWO ? 2 : 1) * blockDim.x) {
+    const int t = t0 + threadIdx.x, t2 = t + blockDim.x;
+    const SlotEval e1 = eval_slot<PAIRED>(p, sm, t, slots, mx);
+    SlotEval e2 = {0.f, 0, false};
+    if (TWO && t2 - lane < slots) e2 = eval_slot<PAIRED>(p, sm, t2, slots, mx);   // warp-uniform condition
+    const unsigned bal1 = __ballot_sync(0xffffffffu, e1.pass), bal2 = TWO ? __ballot_sync(0xffffffffu, e2.pass) : 0u;
+    if (lane == 0) {
+      wcount[warp] = __popc(bal1);
+      if (TWO) wcount2[warp] = __popc(bal2);
+    }
+    __syncthreads();
+    const int v1 = lane < nwarps ? wcount[lane] : 0, v2 = (TWO && lane < nwarps) ? wcount2[lane] : 0;
+    const int total1 = __reduce_add_sync(0xffffffffu, v1), total2 = TWO ? __reduce_add_sync(0xffffffffu, v2) : 0;
+    const int before1 = base + __reduce_add_sync(0xffffffffu, lane < warp ? v1 : 0);
+    const unsigned lower = (1u << lane) - 1u;
+    if (e1.pass) {
+      const int k = before1 + __popc(bal1 & lower);
+      sm.box[k] = slot_box(p, sm, t), sm.score[k] = e1.score, sm.cls[k] = e1.cls;
+    }
+    if (TWO) {
+      const int before2 = base + total1 + __reduce_add_sync(0xffffffffu, lane < warp ? v2 : 0);
+      if (e2.pass) {
+        const int k = before2 + __popc(bal2 & lower);
+        sm.box[k] = slot_box(p, sm, t2), sm.score[k] = e2.score, sm.cls[k] = e2.cls;
       }
     }
-    const unsigned bal = __ballot_sync(0xffffffffu, pass);
-    if (lane == 0) wcount[warp] = __popc(bal);
-    __syncthreads();
-    int before = base, total = 0;
-    for (int w = 0; w < nwarps; ++w) {
-      const int cw = wcount[w];
-      if (w < warp) before += cw;
-      total += cw;
-    }
-    if (pass) {
-      const int k = before + __popc(bal & ((1u << lane) - 1u));
-      sm.box[k] = bx;
-      sm.score[k] = score;
-      sm.cls[k] = best_c;
-    }
-    base += total;
+    base += total1 + total2;
     __syncthreads();
   }
   return base;
+}
+
+template <bool TWO>
+__device__ __forceinline__ int decode_phase(const DecodeParams& p, const Smem& sm) {
+  // lanes 2m, 2m+1 hold the two slots of one cell when B == 2 (slot index and CTA size are even)
+  if (p.B == 2 && !(blockDim.x & 1)) return decode_phase_impl<true, TWO>(p, sm);
+  return decode_phase_impl<false, TWO>(p, sm);
 }
 
 // ---- phase: rank sort + suppression matrix + sweep (utils/utils.py:150-184).  Returns kept count. --------
@@ -243,7 +315,7 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float u, const DecodePa
 template <bool FINITE>
 __device__ __forceinline__ void pair_terms(const float4& A, float area_a, const float4& Bx, bool a_first, float& inter,
                                            float& u) {
-  const float area_b = (Bx.z - Bx.x) * (Bx.w - Bx.y);   // == sm.sarea[j], recomputed: cheaper than the load
+  const float area_b = (Bx.z - Bx.x) * (Bx.w - Bx.y);   // :159 area of box j
   float ww, hh;
   if (FINITE) {
     ww = fmaxf(fminf(Bx.z, A.z) - fmaxf(Bx.x, A.x), 0.f);
@@ -273,12 +345,19 @@ __device__ __forceinline__ void pair_settle(const Smem& sm, int n, int W, int i,
   atomicOr(reinterpret_cast<unsigned*>(sm.misc) + kRowAny + (lo >> 5), 1u << (lo & 31));
 }
 
-// FINITE: every coordinate is below 1e18 in magnitude, so inter and u are finite and not NaN.  fp32 pre-test:
-// inter < fl32(thr_lo u) with a normal product implies inter / u < thr (thr_lo = thr (1 - 2^-20), one rounding of
-// 2^-24), i.e. the pair survives -- the common case, settled without the exact test.
-template <bool FINITE>
-__device__ __forceinline__ bool pair_survives_fast(float inter, float u, float thr_lo) {
-  return FINITE && fmaxf(inter, 1.17549435e-38f) < thr_lo * u;
+// The pair loop's pre-test (tame images only: every |coordinate| < 1e18 and every area in [1e-30, 1e30]).
+// With ta = fl32(thr_lo * area) per box and k = thr_k, the sign of
+//     m = fma(inter, k, -(ta_a + ta_b))            (one fp32 add, one fused multiply-add: exact sign)
+// settles the common case: m < 0  =>  inter (1 + thr_lo) < thr_lo (a_a + a_b) (1 + 3 * 2^-24)
+//                                  =>  inter < thr_lo (1 + 7 * 2^-24) u      (u = fl(fl(a_a + a_b) - inter), inter <= u)
+//                                  =>  inter / u < thr  =>  fl32(inter / u) <= thr: the pair survives (:180).
+// (thr_lo carries a margin of 2^-18 = 64 * 2^-24; an inverted box has inter = 0 and u > 0 and survives as well.)
+// That is 12 instructions per pair instead of 20 for inter, the union and a compare; whatever the sign does not
+// settle (m >= 0: the pair dies or is within 4e-6 of the threshold) takes the exact test.
+__device__ __forceinline__ float pair_margin(const float4& A, float nta_a, const float4& Bx, float ta_b, float k) {
+  const float ww = fmaxf(fminf(Bx.z, A.z) - fmaxf(Bx.x, A.x), 0.f);
+  const float hh = fmaxf(fminf(Bx.w, A.w) - fmaxf(Bx.y, A.y), 0.f);
+  return fmaf(ww * hh, k, nta_a - ta_b);
 }
 
 // DEFER = true: the pair loop notes unsettled columns and works them off per 32-column round (grids of up to 128
@@ -287,70 +366,64 @@ __device__ __forceinline__ bool pair_survives_fast(float inter, float u, float t
 template <bool FINITE, bool DEFER>
 __device__ __forceinline__ void nms_row(const Smem& sm, int n, int W, int i, int d0, int d1, const DecodeParams& p) {
   const float4 A = sm.sbox[i];
-  const float area_i = sm.sarea[i];
   const int jend = i + d1;   // columns may run past n: the head of the sorted boxes is repeated behind their end
-  const float thr_lo = p.thr_lo;
+  auto settle = [&](int c) {   // the exact test of column c (rare on tame images)
+    float in0, u0;
+    pair_terms<FINITE>(A, (A.z - A.x) * (A.w - A.y), sm.sbox[c], c < n, in0, u0);   // :159 area of box i
+    pair_settle(sm, n, W, i, c, in0, u0, p);
+  };
   if constexpr (!FINITE) {   // general code: every pair takes the exact test
-    for (int jj = i + d0; jj <= jend; ++jj) {
-      float in0, u0;
-      pair_terms<false>(A, area_i, sm.sbox[jj], jj < n, in0, u0);
-      pair_settle(sm, n, W, i, jj, in0, u0, p);
-    }
+    for (int jj = i + d0; jj <= jend; ++jj) settle(jj);
   } else if constexpr (!DEFER) {
-    // exact test taken on the spot
+    const float nta = -sm.sta[i], k = p.thr_k;
     int jj = i + d0;
     for (; jj < jend; jj += 2) {   // two columns per trip
-      const float4 B0 = sm.sbox[jj], B1 = sm.sbox[jj + 1];
-      float in0, u0, in1, u1;
-      pair_terms<true>(A, area_i, B0, true, in0, u0);
-      pair_terms<true>(A, area_i, B1, true, in1, u1);
-      const bool ok0 = pair_survives_fast<true>(in0, u0, thr_lo), ok1 = pair_survives_fast<true>(in1, u1, thr_lo);
-      if (ok0 && ok1) continue;
-      if (!ok0) pair_settle(sm, n, W, i, jj, in0, u0, p);
-      if (!ok1) pair_settle(sm, n, W, i, jj + 1, in1, u1, p);
+      const float m0 = pair_margin(A, nta, sm.sbox[jj], sm.sta[jj], k);
+      const float m1 = pair_margin(A, nta, sm.sbox[jj + 1], sm.sta[jj + 1], k);
+      if (fmaxf(m0, m1) < 0.f) continue;
+      if (!(m0 < 0.f)) settle(jj);
+      if (!(m1 < 0.f)) settle(jj + 1);
     }
-    if (jj == jend) {
-      float in0, u0;
-      pair_terms<true>(A, area_i, sm.sbox[jj], true, in0, u0);
-      if (!pair_survives_fast<true>(in0, u0, thr_lo)) pair_settle(sm, n, W, i, jj, in0, u0, p);
-    }
+    if (jj == jend && !(pair_margin(A, nta, sm.sbox[jj], sm.sta[jj], k) < 0.f)) settle(jj);
   } else {
-  // The streaming loop only notes the columns the fp32 pre-test could not settle (one bit each, 32 columns per
-  // round); they are few, and taking the exact test right there would drag the whole warp through ~30
-  // instructions for one or two lanes each time.  After the round the lanes work their notes off together.
-  for (int base = i + d0; base <= jend; base += 32) {
-    const int cend = min(base + 31, jend);
-    unsigned todo = 0;
-    int jj = base;
-    for (; jj < cend; jj += 2) {   // two columns per trip
-      const float4 B0 = sm.sbox[jj], B1 = sm.sbox[jj + 1];
-      float in0, u0, in1, u1;
-      pair_terms<true>(A, area_i, B0, true, in0, u0);
-      pair_terms<true>(A, area_i, B1, true, in1, u1);
-      const bool ok0 = pair_survives_fast<true>(in0, u0, thr_lo), ok1 = pair_survives_fast<true>(in1, u1, thr_lo);
-      if (!(ok0 && ok1)) todo |= ((ok0 ? 0u : 1u) | (ok1 ? 0u : 2u)) << (jj - base);
+    // The streaming loop only notes which columns the pre-test settled (the sign bit of m, shifted into a word:
+    // one funnel shift per column, 32 columns per round); the others are few, and taking the exact test right
+    // there would drag the whole warp through ~30 instructions for one or two lanes each time.  After the round
+    // the lanes work their unsettled columns off together.
+    const float nta = -sm.sta[i], k = p.thr_k;
+    for (int base = i + d0; base <= jend; base += 32) {
+      const int cend = min(base + 31, jend);
+      unsigned sure = 0;   // bit (cend - c) set: column c survives
+      int jj = base;
+      for (; jj < cend; jj += 2) {   // two columns per trip
+        const float m0 = pair_margin(A, nta, sm.sbox[jj], sm.sta[jj], k);
+        const float m1 = pair_margin(A, nta, sm.sbox[jj + 1], sm.sta[jj + 1], k);
+        sure = __funnelshift_l(__float_as_uint(m0), sure, 1);
+        sure = __funnelshift_l(__float_as_uint(m1), sure, 1);
+      }
+      if (jj == cend) sure = __funnelshift_l(__float_as_uint(pair_margin(A, nta, sm.sbox[jj], sm.sta[jj], k)), sure, 1);
+      unsigned todo = ~sure & (0xffffffffu >> (31 - (cend - base)));
+      while (todo) {
+        const int b = __ffs(todo) - 1;
+        todo &= todo - 1;
+        settle(cend - b);
+      }
     }
-    if (jj == cend) {
-      float in0, u0;
-      pair_terms<true>(A, area_i, sm.sbox[jj], true, in0, u0);
-      if (!pair_survives_fast<true>(in0, u0, thr_lo)) todo |= 1u << (jj - base);
-    }
-    while (todo) {
-      const int c = base + __ffs(todo) - 1;
-      todo &= todo - 1;
-      float in0, u0;
-      pair_terms<true>(A, area_i, sm.sbox[c], true, in0, u0);
-      pair_settle(sm, n, W, i, c, in0, u0, p);
-    }
-  }
   }
 }
 
 template <bool FINITE, bool DEFER>
 __device__ __forceinline__ void nms_pairs(const Smem& sm, int n, int W, const DecodeParams& p) {
   const int H = n >> 1;
-  const int G = max(1, (int)blockDim.x / n), K = (H + G - 1) / G;
-  for (int t = threadIdx.x; t < n * G; t += blockDim.x) {   // one round unless n > blockDim (then G == 1)
+  if (2 * n > (int)blockDim.x) {   // one thread per row (the usual case: no division)
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int d1 = (!(n & 1) && i >= H) ? H - 1 : H;
+      if (d1 >= 1) nms_row<FINITE, DEFER>(sm, n, W, i, 1, d1, p);
+    }
+    return;
+  }
+  const int G = (int)blockDim.x / n, K = (H + G - 1) / G;   // few candidates: G threads share a row's offsets
+  for (int t = threadIdx.x; t < n * G; t += blockDim.x) {
     const int g = t / n, i = t - g * n;
     const int d0 = g * K + 1;
     int d1 = min(d0 + K - 1, H);
@@ -376,22 +449,27 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
   // Rank by counting the larger scores, four per shared-memory load.  Without equal scores the ranks are a
   // permutation and add up to n (n - 1) / 2; a smaller sum means ties (rare): those images are ranked again with
   // the tie rule.
-  bool wild = false;   // a NaN, infinite or huge coordinate: the image takes the general pair code
+  bool wild = false;   // a NaN, infinite or huge coordinate, an area that is not an ordinary positive number: the
+                       // image takes the general pair code
   int ranks = 0;
   for (int k = threadIdx.x; k < n; k += blockDim.x) {
     const float s = sm.score[k];
-    int rank = 0;
+    // four independent fp32 counters (one set-on-compare and one add per score; counts < 2^24 are exact)
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
     const int n4 = n & ~3;
     for (int m = 0; m < n4; m += 4) {
       const float4 v = *reinterpret_cast<const float4*>(sm.score + m);
-      rank += (v.x > s) + (v.y > s) + (v.z > s) + (v.w > s);
+      r0 += v.x > s ? 1.f : 0.f, r1 += v.y > s ? 1.f : 0.f, r2 += v.z > s ? 1.f : 0.f, r3 += v.w > s ? 1.f : 0.f;
     }
-    for (int m = n4; m < n; ++m) rank += sm.score[m] > s;
+    for (int m = n4; m < n; ++m) r0 += sm.score[m] > s ? 1.f : 0.f;
+    const int rank = (int)((r0 + r1) + (r2 + r3));
     ranks += rank;
     const float4 b = sm.box[k];
-    wild |= !(fabsf(b.x) < 1.0e18f && fabsf(b.y) < 1.0e18f && fabsf(b.z) < 1.0e18f && fabsf(b.w) < 1.0e18f);
+    const float area = (b.z - b.x) * (b.w - b.y);  // :159
+    wild |= !(fabsf(b.x) < 1.0e18f && fabsf(b.y) < 1.0e18f && fabsf(b.z) < 1.0e18f && fabsf(b.w) < 1.0e18f &&
+              area >= 1.0e-30f && area <= 1.0e30f);
     sm.sbox[rank] = b;
-    sm.sarea[rank] = (b.z - b.x) * (b.w - b.y);  // :159
+    sm.sta[rank] = p.thr_lo * area;   // pair_margin
     sm.sidx[rank] = k;
   }
   ranks = __reduce_add_sync(0xffffffffu, ranks);
@@ -407,13 +485,13 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
       }
       const float4 b = sm.box[k];
       sm.sbox[rank] = b;
-      sm.sarea[rank] = (b.z - b.x) * (b.w - b.y);
+      sm.sta[rank] = p.thr_lo * ((b.z - b.x) * (b.w - b.y));
       sm.sidx[rank] = k;
     }
     __syncthreads();
   }
   // wrap copy: row i reads the columns i+1 .. i+n/2 without a modulo.  It may run over into `box`, which is dead now.
-  for (int r = threadIdx.x; r < (n >> 1); r += blockDim.x) sm.sbox[n + r] = sm.sbox[r];
+  for (int r = threadIdx.x; r < (n >> 1); r += blockDim.x) sm.sbox[n + r] = sm.sbox[r], sm.sta[n + r] = sm.sta[r];
   __syncthreads();
   // suppression matrix: row i, bit j (j > i) set iff box j dies when box i is kept (:166-180)
   if (any_wild)
@@ -449,7 +527,7 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
 
 // ---- kernels ---------------------------------------------------------------------------------------------
 template <typename E, bool DEFER>
-__global__ void decode_nms_kernel(const __grid_constant__ DecodeParams p) {
+__device__ __forceinline__ void decode_nms_image(const DecodeParams& p) {
   extern __shared__ __align__(16) unsigned char raw[];
   Smem sm;
   smem_layout(raw, p.S * p.S * (5 * p.B + p.C), p.max_n, &sm);
@@ -457,7 +535,7 @@ __global__ void decode_nms_kernel(const __grid_constant__ DecodeParams p) {
   load_image<E>(p, n, sm.img);
   nms_prepare(sm, p.max_n);
   __syncthreads();
-  const int cand = decode_phase(p, sm);
+  const int cand = decode_phase<DEFER>(p, sm);
   const int kept = cand > 0 ? nms_phase<DEFER>(sm, cand, p) : 0;
   for (int t = threadIdx.x; t < kept; t += blockDim.x) {
     const int src = sm.keep[t], e = sm.sidx[src];
@@ -480,6 +558,21 @@ __global__ void decode_nms_kernel(const __grid_constant__ DecodeParams p) {
   }
 }
 
+template <typename E, bool DEFER>
+__global__ void decode_nms_kernel(const __grid_constant__ DecodeParams p) {
+  decode_nms_image<E, DEFER>(p);
+}
+// grids of up to 128 candidates run 96-thread CTAs, 16 to an SM: 40 registers (the pair loop would take 48 unbounded)
+template <>
+__global__ void __launch_bounds__(96, 16) decode_nms_kernel<float, true>(const __grid_constant__ DecodeParams p) {
+  decode_nms_image<float, true>(p);
+}
+template <>
+__global__ void __launch_bounds__(96, 16)
+    decode_nms_kernel<__nv_bfloat16, true>(const __grid_constant__ DecodeParams p) {
+  decode_nms_image<__nv_bfloat16, true>(p);
+}
+
 template <typename E>
 __global__ void decode_kernel(const __grid_constant__ DecodeParams p) {
   extern __shared__ __align__(16) unsigned char raw[];
@@ -488,7 +581,7 @@ __global__ void decode_kernel(const __grid_constant__ DecodeParams p) {
   const int64_t n = blockIdx.x;
   load_image<E>(p, n, sm.img);
   __syncthreads();
-  const int cand = decode_phase(p, sm);
+  const int cand = decode_phase<false>(p, sm);
   for (int t = threadIdx.x; t < cand; t += blockDim.x) {
     const int64_t dst = n * p.max_n + t;
     reinterpret_cast<float4*>(p.boxes)[dst] = sm.box[t];
@@ -505,7 +598,7 @@ __global__ void decode_kernel(const __grid_constant__ DecodeParams p) {
 }
 
 template <bool DEFER>
-__global__ void nms_kernel(const __grid_constant__ DecodeParams p) {
+__device__ __forceinline__ void nms_image(const DecodeParams& p) {
   extern __shared__ __align__(16) unsigned char raw[];
   Smem sm;
   smem_layout(raw, 0, p.max_n, &sm);
@@ -525,6 +618,15 @@ __global__ void nms_kernel(const __grid_constant__ DecodeParams p) {
   for (int t = threadIdx.x; t < p.max_n; t += blockDim.x)
     p.keep[n * p.max_n + t] = t < kept ? sm.sidx[sm.keep[t]] : 0;
   if (threadIdx.x == 0) p.out_counts[n] = kept;
+}
+
+template <bool DEFER>
+__global__ void nms_kernel(const __grid_constant__ DecodeParams p) {
+  nms_image<DEFER>(p);
+}
+template <>
+__global__ void __launch_bounds__(96, 16) nms_kernel<true>(const __grid_constant__ DecodeParams p) {
+  nms_image<true>(p);
 }
 
 // run_test_mAP post-processing (utils/utils.py:406-407, :347-354): clamp to [0,1], scale to pixels in fp32,
@@ -568,7 +670,7 @@ int check_decode_args(const void* pred, const int64_t st[4], int dtype, int64_t 
 void set_threshold(DecodeParams& p, float thr) {
   p.iou_thr = thr;
   p.thr_fast = (thr >= 0.f && thr < 1.0e30f) ? 1 : 0;
-  p.thr_mid = 0.0, p.thr_tie_ok = 0, p.thr_lo = 0.f;
+  p.thr_mid = 0.0, p.thr_tie_ok = 0, p.thr_lo = 0.f, p.thr_k = 1.f;
   if (p.thr_fast) {
     const float up = nextafterf(thr, INFINITY);
     p.thr_mid = 0.5 * ((double)thr + (double)up);
@@ -577,7 +679,10 @@ void set_threshold(DecodeParams& p, float thr) {
     p.thr_tie_ok = (bits & 1u) == 0u;   // ties round to the even mantissa
     // `x <= mid u` as `x < mid' u` with mid' two doubles above mid (see iou_exceeds)
     if (p.thr_tie_ok) p.thr_mid = nextafter(nextafter(p.thr_mid, INFINITY), INFINITY);
-    p.thr_lo = nextafterf((float)((double)thr * (1.0 - 0x1p-20)), 0.f);
+    if (thr >= 0x1p-20f && thr <= 4.f) {   // pair_margin: range in which its products stay ordinary numbers
+      p.thr_lo = nextafterf((float)((double)thr * (1.0 - 0x1p-18)), 0.f);
+      p.thr_k = nextafterf((float)(1.0 + (double)p.thr_lo), INFINITY);
+    }
   }
 }
 
@@ -589,6 +694,9 @@ void fill_decode(DecodeParams& p, const void* pred, const int64_t st[4], int S, 
   p.cs = (float)(1.0 / (double)S);
   p.thresh = thresh;
   p.max_n = S * S * B;
+  p.s_magic = (65536 + S - 1) / S;
+  for (int cell = 0; cell < S * S; ++cell)
+    if ((int)(((unsigned)cell * (unsigned)p.s_magic) >> 16) != cell / S) p.s_magic = 0;
 }
 
 }  // namespace
