@@ -23,6 +23,12 @@
 namespace yolo1 {
 namespace {
 
+// Unroll factors of the hot loops, from measurement (tools/tune_decode.py on B200, M images/s at S=7 N=65536 uniform /
+// sigmoid inputs, S=14 N=16384): the compiler's own choice for the rank loop 133.7 / 166.7; rank x4 148.8 / 187.1;
+// plus the deferred pair loop rolled (x1) 151.7 / 192.8 (x4: 148.8); the on-the-spot pair loop x4 11.73 at S=14
+// (rolled 11.18).  The kernel is sensitive to its code size (ncu: no_instruction stalls), not only to its
+// instruction count.
+constexpr int kRankUnroll = 4, kPairUnroll = 1, kPair2Unroll = 4;
 constexpr int kMaxCand = 1024;
 constexpr int kRowAny = 64, kRankSum = 96;   // slots of Smem::misc (nms_phase)
 
@@ -377,6 +383,7 @@ __device__ __forceinline__ void nms_row(const Smem& sm, int n, int W, int i, int
   } else if constexpr (!DEFER) {
     const float nta = -sm.sta[i], k = p.thr_k;
     int jj = i + d0;
+#pragma unroll kPair2Unroll
     for (; jj < jend; jj += 2) {   // two columns per trip
       const float m0 = pair_margin(A, nta, sm.sbox[jj], sm.sta[jj], k);
       const float m1 = pair_margin(A, nta, sm.sbox[jj + 1], sm.sta[jj + 1], k);
@@ -395,6 +402,7 @@ __device__ __forceinline__ void nms_row(const Smem& sm, int n, int W, int i, int
       const int cend = min(base + 31, jend);
       unsigned sure = 0;   // bit (cend - c) set: column c survives
       int jj = base;
+#pragma unroll kPairUnroll
       for (; jj < cend; jj += 2) {   // two columns per trip
         const float m0 = pair_margin(A, nta, sm.sbox[jj], sm.sta[jj], k);
         const float m1 = pair_margin(A, nta, sm.sbox[jj + 1], sm.sta[jj + 1], k);
@@ -457,6 +465,7 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
     // four independent fp32 counters (one set-on-compare and one add per score; counts < 2^24 are exact)
     float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
     const int n4 = n & ~3;
+#pragma unroll kRankUnroll
     for (int m = 0; m < n4; m += 4) {
       const float4 v = *reinterpret_cast<const float4*>(sm.score + m);
       r0 += v.x > s ? 1.f : 0.f, r1 += v.y > s ? 1.f : 0.f, r2 += v.z > s ? 1.f : 0.f, r3 += v.w > s ? 1.f : 0.f;
