@@ -30,7 +30,7 @@ namespace {
 // instruction count.
 constexpr int kRankUnroll = 4, kPairUnroll = 1, kPair2Unroll = 4;
 constexpr int kMaxCand = 1024;
-constexpr int kRowAny = 64, kRankSum = 96;   // slots of Smem::misc (nms_phase)
+constexpr int kKeepA = 64, kRankSum = 96, kKeepB = 128;   // slots of Smem::misc (nms_phase): kept-set words, checksum
 
 struct DecodeParams {
   const void* pred;
@@ -77,8 +77,8 @@ struct Smem {
   float* sta;       // [max_n + max_n/2]  thr_lo * area of the sorted boxes, wrapped like sbox
   int32_t* sidx;    // [max_n]  sorted position -> emission index
   int32_t* keep;    // [max_n]  kept sorted positions
-  int32_t* misc;    // [160]  0..63 decode scratch / kept count; 64..95 rows-with-bits words; 96 rank checksum;
-                    //        128..159 decode scratch
+  int32_t* misc;    // [160]  0..63 decode scratch / kept count; 64..95 and 128..159 kept-set words of the sweep
+                    //        (128..159 decode scratch before); 96 rank checksum
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
@@ -347,8 +347,7 @@ __device__ __forceinline__ void pair_settle(const Smem& sm, int n, int W, int i,
   const int j = jj < n ? jj : jj - n;
   const int lo = min(i, j), hi = max(i, j);
   if (p.per_class && sm.cls[sm.sidx[lo]] != sm.cls[sm.sidx[hi]]) return;
-  atomicOr(&sm.mask[lo * W + (hi >> 5)], 1u << (hi & 31));
-  atomicOr(reinterpret_cast<unsigned*>(sm.misc) + kRowAny + (lo >> 5), 1u << (lo & 31));
+  atomicOr(&sm.mask[hi * W + (lo >> 5)], 1u << (lo & 31));   // column hi: the earlier boxes that kill it
 }
 
 // The pair loop's pre-test (tame images only: every |coordinate| < 1e18 and every area in [1e-30, 1e30]).
@@ -441,15 +440,105 @@ __device__ __forceinline__ void nms_pairs(const Smem& sm, int n, int W, const De
   }
 }
 
+// ---- sweep (utils/utils.py:162-182): which boxes does the greedy loop keep? --------------------------------
+// The matrix holds, for every box j (sorted position), the earlier boxes that kill it if they are kept: column j,
+// bit i (i < j).  The greedy result is the one set K with  K(j) = no i < j with K(i) and M[i][j];  it is reached by
+// re-evaluating that line for all j at once until nothing changes: an index whose predecessors are settled settles
+// with the next pass, so the number of passes is the depth of the kill chains (a handful), not the number of kept
+// boxes -- and a pass is a few bit operations per box, with no serial walk over shared memory.
+__device__ __forceinline__ unsigned valid_word(int n, int W, int w) {
+  return (w == W - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+}
+
+// kept-set words -> sm.keep (sorted positions of the kept boxes, ascending) and the count; warp 0
+__device__ __forceinline__ void emit_keep(const Smem& sm, int W, int lane, const unsigned* K) {
+  int kept = 0;
+  for (int w = 0; w < W; ++w) {
+    const unsigned a = K[w];
+    if ((a >> lane) & 1u) sm.keep[kept + __popc(a & ((1u << lane) - 1u))] = (w << 5) + lane;
+    kept += __popc(a);
+  }
+  if (lane == 0) sm.misc[0] = kept;
+}
+
+template <bool SMALL>
+__device__ __forceinline__ int sweep_phase(const Smem& sm, int n, int W) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if constexpr (SMALL) {
+    // up to 128 boxes: one warp, the columns of lane, lane + 32, ... and the kept set in registers; a pass updates
+    // word after word, so later words already see the new earlier ones
+    if (warp == 0) {
+      unsigned col[4][4], K[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = lane + 32 * c;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) col[c][w] = (w <= c && c < W && j < n) ? sm.mask[j * W + w] : 0u;
+        K[c] = c < W ? valid_word(n, W, c) : 0u;
+      }
+      bool changed;
+      do {
+        changed = false;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (c < W) {
+            unsigned hit = 0;
+#pragma unroll
+            for (int w = 0; w <= c; ++w) hit |= K[w] & col[c][w];
+            const unsigned nk = __ballot_sync(0xffffffffu, hit == 0u) & valid_word(n, W, c);
+            changed |= nk != K[c];
+            K[c] = nk;
+          }
+        }
+      } while (changed);
+      int kept = 0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {   // (K stays in registers: no run-time index)
+        if ((K[c] >> lane) & 1u) sm.keep[kept + __popc(K[c] & ((1u << lane) - 1u))] = (c << 5) + lane;
+        kept += __popc(K[c]);
+      }
+      if (lane == 0) sm.misc[0] = kept;
+    }
+  } else {
+    // up to 1024 boxes: every thread re-evaluates its columns against the kept set of the previous pass (two
+    // copies of the set in shared memory, one barrier per pass)
+    unsigned* cur = reinterpret_cast<unsigned*>(sm.misc) + kKeepA;
+    unsigned* nxt = reinterpret_cast<unsigned*>(sm.misc) + kKeepB;
+    if ((int)threadIdx.x < W) cur[threadIdx.x] = valid_word(n, W, threadIdx.x);
+    __syncthreads();
+    while (true) {
+      bool changed = false;
+      for (int j = threadIdx.x; j < (W << 5); j += blockDim.x) {   // a warp covers one word of columns per trip
+        const int wj = j >> 5;
+        unsigned hit = 0;
+        if (j < n) {
+          const unsigned* c = sm.mask + j * W;
+          for (int w = 0; w <= wj; ++w) hit |= cur[w] & c[w];
+        }
+        const unsigned nk = __ballot_sync(0xffffffffu, j < n && hit == 0u);
+        if (lane == 0) nxt[wj] = nk;
+        changed |= nk != cur[wj];
+      }
+      const int any = __syncthreads_or(changed);
+      unsigned* t = cur;
+      cur = nxt, nxt = t;
+      if (!any) break;
+    }
+    if (warp == 0) emit_keep(sm, W, lane, cur);
+  }
+  __syncthreads();
+  return sm.misc[0];
+}
+
 // before the barrier that precedes nms_phase: clear what the phase accumulates into with atomics
 __device__ __forceinline__ void nms_prepare(const Smem& sm, int max_n) {
-  if (threadIdx.x < 33) sm.misc[kRowAny + threadIdx.x] = 0;   // 32 row words + the rank checksum
+  if (threadIdx.x == 0) sm.misc[kRankSum] = 0;
   for (int t = threadIdx.x; t < max_n; t += blockDim.x) sm.sidx[t] = 0;   // NaN scores leave holes: keep them in range
 }
 
 template <bool DEFER>
 __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodeParams& p) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
   const int W = (n + 31) >> 5;
   // the suppression matrix starts empty; dead pairs are OR-ed in below
   for (int t = threadIdx.x; t < n * W; t += blockDim.x) sm.mask[t] = 0u;
@@ -502,36 +591,13 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
   // wrap copy: row i reads the columns i+1 .. i+n/2 without a modulo.  It may run over into `box`, which is dead now.
   for (int r = threadIdx.x; r < (n >> 1); r += blockDim.x) sm.sbox[n + r] = sm.sbox[r], sm.sta[n + r] = sm.sta[r];
   __syncthreads();
-  // suppression matrix: row i, bit j (j > i) set iff box j dies when box i is kept (:166-180)
+  // suppression matrix: column j, bit i (i < j) set iff box j dies when box i is kept (:166-180)
   if (any_wild)
     nms_pairs<false, false>(sm, n, W, p);
   else
     nms_pairs<true, DEFER>(sm, n, W, p);
   __syncthreads();
-  // sweep: warp 0 walks the sorted boxes word by word; lane w owns word w of the removed set (n <= 1024 -> W <= 32).
-  // A kept box whose row is empty changes nothing, so only the live boxes with a non-empty row (misc[kRowAny]) are
-  // visited one after the other; what is left of `alive` at the end of a word are its kept boxes.
-  if (warp == 0) {
-    unsigned removed = 0;
-    int kept = 0;
-    for (int w = 0; w < W; ++w) {
-      const unsigned valid = (w == W - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
-      unsigned alive = ~__shfl_sync(0xffffffffu, removed, w) & valid;
-      unsigned todo = alive & (unsigned)sm.misc[kRowAny + w];
-      while (todo) {
-        const int b = __ffs(todo) - 1;
-        const unsigned* row = sm.mask + ((w << 5) + b) * W;
-        if (lane > w && lane < W) removed |= row[lane];
-        alive &= ~row[w];                   // bits above b only (j > i)
-        todo &= alive & (0xfffffffeu << b);  // drop b, what is before it and what just died
-      }
-      if ((alive >> lane) & 1u) sm.keep[kept + __popc(alive & ((1u << lane) - 1u))] = (w << 5) + lane;
-      kept += __popc(alive);
-    }
-    if (lane == 0) sm.misc[0] = kept;
-  }
-  __syncthreads();
-  return sm.misc[0];
+  return sweep_phase<DEFER>(sm, n, W);
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------------
