@@ -69,11 +69,10 @@ struct DecodeParams {
 struct Smem {
   float* img;       // [S*S*D]   (decode)   -- aliased by mask after decode
   uint32_t* mask;   // [n * W]
-  float4* box;      // [max_n]  candidates in emission order; dead after the sort, then the tail of sbox's wrap copy
+  float4* box;      // [max_n]  candidates in emission order
   float* score;     // [max_n]
   int32_t* cls;     // [max_n]
-  float4* sbox;     // [max_n]  sorted by score; after the sort sbox[n + r] = sbox[r] for r < n/2 (wrap-free reads),
-                    //          which runs over into `box`
+  float4* sbox;     // [max_n + max_n/2]  sorted by score, sbox[n + r] = sbox[r] for r < n/2 (wrap-free reads)
   float* sta;       // [max_n + max_n/2]  thr_lo * area of the sorted boxes, wrapped like sbox
   int32_t* sidx;    // [max_n]  sorted position -> emission index
   int32_t* keep;    // [max_n]  kept sorted positions
@@ -92,8 +91,8 @@ __host__ __device__ inline size_t smem_layout(unsigned char* base, int img_float
   if (s) s->img = reinterpret_cast<float*>(base), s->mask = reinterpret_cast<uint32_t*>(base);
   off += align16(region);
   if (s) s->sbox = reinterpret_cast<float4*>(base + off);
-  off += (size_t)max_n * 16;
-  if (s) s->box = reinterpret_cast<float4*>(base + off);   // directly behind sbox: see the wrap copy in nms_phase
+  off += (size_t)(max_n + max_n / 2) * 16;
+  if (s) s->box = reinterpret_cast<float4*>(base + off);
   off += (size_t)max_n * 16;
   if (s) s->score = reinterpret_cast<float*>(base + off);
   off += align16((size_t)max_n * 4);
@@ -178,7 +177,8 @@ struct SlotEval {   // what a slot carries across the barrier of its pass; the b
 // One (cell, slot) of the image.  PAIRED (B == 2): the two slots of a cell sit in neighbouring lanes, so each lane
 // scans half of the class scores and the halves are merged with one shuffle (every lane of the warp must call).
 template <bool PAIRED>
-__device__ __forceinline__ SlotEval eval_slot(const DecodeParams& p, const Smem& sm, int t, int slots, float mx) {
+__device__ __forceinline__ SlotEval eval_slot(const DecodeParams& p, const Smem& sm, int t, int slots, float mx,
+                                             bool use_mx) {
   const int B = p.B, C = p.C, D = 5 * B + C;
   SlotEval r = {0.f, 0, false};
   const bool live = t < slots;
@@ -212,7 +212,7 @@ __device__ __forceinline__ SlotEval eval_slot(const DecodeParams& p, const Smem&
     }
   }
   const float conf = P[b];
-  if (live && (conf > 0.0001f || conf == mx)) {  // :108-114
+  if (live && (conf > 0.0001f || (use_mx && conf == mx))) {  // :108-114
     r.score = conf * best_p;                      // :129
     r.cls = best_c;
     r.pass = (double)r.score > p.thresh;
@@ -240,7 +240,10 @@ __device__ __forceinline__ int decode_phase_impl(const DecodeParams& p, const Sm
   float* red = reinterpret_cast<float*>(sm.misc);  // [32] floats
   int* wcount = sm.misc + 32;                      // [32] ints: first round of a pass; wcount2: second round
   int* wcount2 = sm.misc + 128;
-  // :109-113 max over the confidences of the image
+  // :109-113 max over the confidences of the image.  It only matters when no confidence exceeds 0.0001 (a slot at
+  // or below that is a candidate iff it equals the maximum), so the per-warp maxima travel with the first pass's
+  // counts through the same barrier, the pass is evaluated without the rule, and it is repeated with the rule in
+  // the rare image that needs it.
   float mx = -INFINITY;
   for (int t = threadIdx.x; t < slots; t += blockDim.x) {
     int cell, b;
@@ -249,24 +252,29 @@ __device__ __forceinline__ int decode_phase_impl(const DecodeParams& p, const Sm
   }
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
-  __syncthreads();
-  mx = warp_max(lane < nwarps ? red[lane] : -INFINITY);
+  bool have_mx = false;
 
   // TWO: two rounds of slots per pass (slot t and slot t + blockDim).  With 98 slots on 96 threads the second round
   // is two slots in the first warp, and one pass means one barrier pair and one prefix.  (Not for the large-grid
   // kernel: carrying the second slot across the barrier costs it 4 registers and with them a resident CTA.)
   int base = 0;  // candidates emitted by earlier passes (uniform)
-  for (int t0 = 0; t0 < slots; t0 += (TWO ? 2 : 1) * blockDim.x) {
+  const int stride = (TWO ? 2 : 1) * blockDim.x;
+  for (int t0 = 0; t0 < slots;) {
     const int t = t0 + threadIdx.x, t2 = t + blockDim.x;
-    const SlotEval e1 = eval_slot<PAIRED>(p, sm, t, slots, mx);
+    const SlotEval e1 = eval_slot<PAIRED>(p, sm, t, slots, mx, have_mx);
     SlotEval e2 = {0.f, 0, false};
-    if (TWO && t2 - lane < slots) e2 = eval_slot<PAIRED>(p, sm, t2, slots, mx);   // warp-uniform condition
+    if (TWO && t2 - lane < slots) e2 = eval_slot<PAIRED>(p, sm, t2, slots, mx, have_mx);   // warp-uniform condition
     const unsigned bal1 = __ballot_sync(0xffffffffu, e1.pass), bal2 = TWO ? __ballot_sync(0xffffffffu, e2.pass) : 0u;
     if (lane == 0) {
       wcount[warp] = __popc(bal1);
       if (TWO) wcount2[warp] = __popc(bal2);
     }
     __syncthreads();
+    if (!have_mx) {
+      mx = warp_max(lane < nwarps ? red[lane] : -INFINITY);
+      have_mx = true;
+      if (!(mx > 0.0001f)) continue;   // uniform: this pass again, now with the `== max` rule
+    }
     const int v1 = lane < nwarps ? wcount[lane] : 0, v2 = (TWO && lane < nwarps) ? wcount2[lane] : 0;
     const int total1 = __reduce_add_sync(0xffffffffu, v1), total2 = TWO ? __reduce_add_sync(0xffffffffu, v2) : 0;
     const int before1 = base + __reduce_add_sync(0xffffffffu, lane < warp ? v1 : 0);
@@ -283,6 +291,7 @@ __device__ __forceinline__ int decode_phase_impl(const DecodeParams& p, const Sm
       }
     }
     base += total1 + total2;
+    t0 += stride;
     __syncthreads();
   }
   return base;
@@ -566,9 +575,10 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
     const float area = (b.z - b.x) * (b.w - b.y);  // :159
     wild |= !(fabsf(b.x) < 1.0e18f && fabsf(b.y) < 1.0e18f && fabsf(b.z) < 1.0e18f && fabsf(b.w) < 1.0e18f &&
               area >= 1.0e-30f && area <= 1.0e30f);
-    sm.sbox[rank] = b;
-    sm.sta[rank] = p.thr_lo * area;   // pair_margin
-    sm.sidx[rank] = k;
+    const float ta = p.thr_lo * area;   // pair_margin
+    sm.sbox[rank] = b, sm.sta[rank] = ta, sm.sidx[rank] = k;
+    // wrap copy: row i reads the columns i+1 .. i+n/2 without a modulo
+    if (rank < (n >> 1)) sm.sbox[n + rank] = b, sm.sta[n + rank] = ta;
   }
   ranks = __reduce_add_sync(0xffffffffu, ranks);
   if (lane == 0 && ranks) atomicAdd(&sm.misc[kRankSum], ranks);
@@ -582,15 +592,12 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
         rank += (v > s) || (v == s && m < k);
       }
       const float4 b = sm.box[k];
-      sm.sbox[rank] = b;
-      sm.sta[rank] = p.thr_lo * ((b.z - b.x) * (b.w - b.y));
-      sm.sidx[rank] = k;
+      const float ta = p.thr_lo * ((b.z - b.x) * (b.w - b.y));
+      sm.sbox[rank] = b, sm.sta[rank] = ta, sm.sidx[rank] = k;
+      if (rank < (n >> 1)) sm.sbox[n + rank] = b, sm.sta[n + rank] = ta;
     }
     __syncthreads();
   }
-  // wrap copy: row i reads the columns i+1 .. i+n/2 without a modulo.  It may run over into `box`, which is dead now.
-  for (int r = threadIdx.x; r < (n >> 1); r += blockDim.x) sm.sbox[n + r] = sm.sbox[r], sm.sta[n + r] = sm.sta[r];
-  __syncthreads();
   // suppression matrix: column j, bit i (i < j) set iff box j dies when box i is kept (:166-180)
   if (any_wild)
     nms_pairs<false, false>(sm, n, W, p);
