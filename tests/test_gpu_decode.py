@@ -180,6 +180,44 @@ def test_nms_semantics():
             assert np.array_equal(y.nms(b, s, thr).numpy(), O.nms(b.numpy(), s.numpy(), thr)), (n, thr)
 
 
+def test_nms_long_kill_chains():
+    """Box i overlaps box i+1 above the threshold and box i+2 below it, scores descending: the greedy loop keeps
+    0, 2, 4, ... -- a kill chain as deep as the set.  The sweep re-evaluates all boxes per pass ("sweep as
+    a fixed point") and settles about two per pass here, so this is its worst case: every size class of the kernels
+    (one-warp sweep up to 128 boxes, CTA-wide above), through the raw call and through the fused decode."""
+    y = _y()
+    for n in (2, 3, 33, 64, 97, 98, 128, 129, 392, 1024):
+        x0 = np.arange(n, dtype=np.float32) * np.float32(0.25)          # IoU(i, i+1) = 0.6, IoU(i, i+2) = 1/3
+        b = np.stack([x0, np.zeros(n, np.float32), x0 + 1, np.ones(n, np.float32)], 1)
+        s = (1.0 - np.arange(n) / (2.0 * n)).astype(np.float32)
+        want = O.nms(b, s, 0.5)
+        assert want.tolist() == list(range(0, n, 2))
+        assert y.nms(torch.from_numpy(b), torch.from_numpy(s), 0.5).tolist() == want.tolist(), n
+        # chains that break and restart: every 7th box is far away
+        b2 = b.copy()
+        b2[::7, 1] += 5
+        b2[::7, 3] += 5
+        assert np.array_equal(y.nms(torch.from_numpy(b2), torch.from_numpy(s), 0.5).numpy(), O.nms(b2, s, 0.5)), n
+    # the same chain inside a decoded image: 49 cells x 2 slots, all boxes on one row of overlapping squares
+    S = 7
+    pred = torch.zeros(1, S, S, 30)
+    k = 0
+    for i in range(S):
+        for j in range(S):
+            for bslot in range(2):
+                pred[0, i, j, bslot] = 0.99 - 0.005 * k                  # descending confidences
+                cx = 0.05 + 0.004 * k                                    # centres 0.004 apart, width 0.016: IoU 0.6 / 0.33
+                pred[0, i, j, 2 + 4 * bslot] = (cx * S - j)
+                pred[0, i, j, 3 + 4 * bslot] = (0.5 * S - i)
+                pred[0, i, j, 4 + 4 * bslot] = 0.016
+                pred[0, i, j, 5 + 4 * bslot] = 0.5
+                k += 1
+            pred[0, i, j, 10] = 1.0
+    orc = O.decode_nms(pred.numpy(), thresh=0.1, nms_th=0.5)
+    assert 40 <= int(orc["counts"][0]) <= 60
+    _assert_batched_equal(y.decode_nms_batched(pred.cuda(), 0.1, 0.5, return_keep=True), orc, "chain image")
+
+
 def test_nms_threshold_boundaries():
     """`ovr <= threshold` (utils/utils.py:180) is evaluated without the division in the kernel (iou_exceeds): pairs
     whose fp32 quotient is exactly the threshold, one ulp above and one ulp below must fall on the right side.

@@ -90,3 +90,70 @@ def test_synth_targets_follow_the_encoder_format():
     assert float(pred.min()) >= 0.01 and float(pred.max()) <= 0.99
     p2, n = synth.make_tie_free_decode_inputs(128, 7, seed=2)
     assert synth.score_tie_images(p2).numel() == 0 and n >= 0
+
+
+# ---- properties the decode+NMS kernel's design rests on (DESIGN.md, K2+K3), checked here without a GPU -------------
+def test_fixed_point_passes_reach_the_greedy_keep_set():
+    """Sweep as a fixed point: K(j) = no i < j with K(i) and M[i][j], re-evaluated for all j until nothing changes,
+    gives exactly what the reference's greedy loop keeps (utils/utils.py:162-182), whatever the kill matrix."""
+    rng = np.random.RandomState(3)
+    for trial in range(300):
+        n = int(rng.randint(1, 140))
+        dens = rng.choice([0.0, 0.02, 0.1, 0.5, 1.0])
+        M = np.triu(rng.rand(n, n) < dens, 1)                     # M[i][j], i < j: j dies if i is kept
+        if trial % 10 == 0:                                       # a full chain: i kills i+1
+            M = np.zeros((n, n), bool)
+            M[np.arange(n - 1), np.arange(1, n)] = True
+        greedy = np.ones(n, bool)
+        for i in range(n):
+            if greedy[i]:
+                greedy[M[i]] = False
+        K = np.ones(n, bool)
+        passes = 0
+        while True:
+            newK = ~(M & K[:, None]).any(0)
+            passes += 1
+            if np.array_equal(newK, K):
+                break
+            K = newK
+        assert np.array_equal(K, greedy), (trial, n, dens)
+        assert passes <= n + 1
+
+
+def test_pair_pretest_never_settles_a_pair_that_dies():
+    """The pair loop's fp32 pre-test (decode_nms.cu, pair_margin): m = fma(inter, k, -(ta_a + ta_b)) < 0 must imply
+    fl32(inter / u) <= thr, the reference's survival test (utils/utils.py:179-180), for the constants
+    set_threshold() derives.  numpy float32 emulation (the fma in float64: inter * k is exact there)."""
+    f = np.float32
+    rng = np.random.RandomState(5)
+
+    def check(thr, A, B):
+        thr = f(thr)
+        thr_lo = np.nextafter(f(np.float64(thr) * (1 - 2.0 ** -18)), f(0))
+        k = np.nextafter(f(1.0 + np.float64(thr_lo)), f(np.inf))
+        aa = (A[:, 2] - A[:, 0]) * (A[:, 3] - A[:, 1])
+        ab = (B[:, 2] - B[:, 0]) * (B[:, 3] - B[:, 1])
+        tame = (aa >= f(1e-30)) & (ab >= f(1e-30)) & (aa <= f(1e30)) & (ab <= f(1e30))
+        ww = np.maximum(np.minimum(B[:, 2], A[:, 2]) - np.maximum(B[:, 0], A[:, 0]), f(0))
+        hh = np.maximum(np.minimum(B[:, 3], A[:, 3]) - np.maximum(B[:, 1], A[:, 1]), f(0))
+        inter = ww * hh
+        R = (-(thr_lo * aa)) - (thr_lo * ab)
+        settled = (inter.astype(np.float64) * np.float64(k) + R.astype(np.float64)) < 0
+        with np.errstate(all="ignore"):
+            survives = inter / ((aa + ab) - inter) <= thr
+        assert not (tame & settled & ~survives).any(), thr
+        return (tame & settled).sum(), (tame & survives).sum()
+
+    n = 200_000
+    for thr in (0.5, 0.45, 0.1, 1.0, 0.99999, 2.0 ** -20, 4.0, 0.3, 0.005):
+        c, wh = rng.rand(n, 2).astype(f), rng.rand(n, 2).astype(f)
+        A = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(f)
+        B = (A + rng.randn(n, 4) * rng.choice([1e-3, 1e-2, 0.1, 0.5], (n, 1))).astype(f)
+        settled, survive = check(thr, A, B)
+        assert settled >= 0.999 * survive                       # ... and it settles practically every survivor
+        check(thr, A * f(1e-14), B * f(1e-14))                  # tiny and huge boxes
+        check(thr, A * f(1e14), B * f(1e14))
+        s = np.exp(rng.uniform(-30, 30, n)).astype(f)            # IoU within +-40 ulp of the threshold
+        t = np.clip(f(thr) * (1 + rng.randint(-40, 40, n) * 2.0 ** -23), 0, 1).astype(f)
+        z = np.zeros(n, f)
+        check(thr, np.stack([z, z, s, s], 1), np.stack([z, z, s, (s * t).astype(f)], 1))

@@ -6,14 +6,15 @@
 //
 // One CTA per image; an image's candidates never leave shared memory in the fused kernel:
 //   load   : the image's S*S*D values -> shared (coalesced)
-//   decode : max confidence (block reduce), per (cell, slot) candidate test, class arg-max, score,
-//            `double(score) > thresh`, order-preserving compaction (ballot + prefix) = emission order
+//   decode : per (cell, slot) candidate test, class arg-max (the two slots of a cell share the scan), score,
+//            `double(score) > thresh`, order-preserving compaction (ballot + prefix) = emission order; the image's
+//            maximum confidence rides on the same barrier (it only matters when no confidence exceeds 1e-4)
 //   sort   : rank by counting (score descending, emission index ascending) -- deterministic, no ties left
-//   mask   : suppression bit-matrix; one thread per unordered pair (wrapped-diagonal enumeration, no idle lanes),
-//            the rare dead pair ORs its bit in (dies iff !(IoU <= thr), utils/utils.py:180; the image tile is
-//            reused for the matrix)
-//   sweep  : one warp walks the sorted boxes word by word; lane w holds word w of the removed-set; a kept
-//            box ORs its row in.  A suppressed box never suppresses (iterated semantics of the reference).
+//   mask   : suppression bit-matrix; one thread per row of the unordered pairs (wrapped-diagonal enumeration, no idle
+//            lanes); an fp32 pre-test settles the surviving pairs, the rare dead pair ORs its bit in (dies iff
+//            !(IoU <= thr), utils/utils.py:180; the image tile is reused for the matrix)
+//   sweep  : the kept set as the fixed point of K(j) = no i < j with K(i) and M[i][j], a few passes of bit
+//            operations.  A suppressed box never suppresses (iterated semantics of the reference).
 //   store  : kept detections in descending score order (float4 boxes), counts.
 #include <math.h>
 #include <string.h>
