@@ -325,8 +325,10 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float u, const DecodePa
 // consecutive boxes (conflict-free 128-bit loads).  When the CTA has room for several threads per row
 // (blockDim >= 2 n) the offsets are split between them.  The few pairs that die set their bit with a
 // shared-memory atomic OR; the earlier box of the pair (lower sorted position) plays the reference's box i.
-// FINITE = true: every coordinate of the image is an ordinary number (|c| < 1e18), so clamp(min=)/clamp(max=) are
-// plain max/min (one FMNMX each), the intersection is symmetric in the two boxes and nothing overflows.
+// The bit lands in the later box's column (column j, bit i: kept i kills j), which is what the sweep reads.
+// FINITE = true: every coordinate of the image is an ordinary number (|c| < 1e18) and every area lies in
+// [1e-30, 1e30], so clamp(min=)/clamp(max=) are plain max/min (one FMNMX each), the intersection is symmetric in
+// the two boxes, nothing overflows or underflows, and the fp32 pre-test (pair_margin) applies.
 // intersection and union term of box A (area_a) with box Bx, by the reference's op sequence (:166-179)
 template <bool FINITE>
 __device__ __forceinline__ void pair_terms(const float4& A, float area_a, const float4& Bx, bool a_first, float& inter,
