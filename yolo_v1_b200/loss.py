@@ -117,13 +117,17 @@ def yolo_loss_from_objects(pred, boxes, labels, offsets, batch_size, S=None, B=2
         status = torch.empty(1, dtype=torch.int32, device=dev)
         ws_bytes = int(L.yolo1_loss_objects_workspace_bytes(N, S, B, C))
         ws = workspace if workspace is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if ws.numel() * ws.element_size() < ws_bytes:
+            raise ValueError("workspace too small: need %d bytes" % ws_bytes)
+        if grad is not None and (grad.shape != pred.shape or grad.dtype != pred.dtype or grad.device != dev):
+            raise ValueError("out_grad must match pred in shape, dtype and device")
         rc = L.yolo1_loss_fwd_bwd_objects_ex(
             pred.data_ptr(), _lib.strides4(pred), _dtype_code(pred), int(bool(from_logits)),
             boxes.data_ptr() if boxes.numel() else None, labels.data_ptr() if labels.numel() else None,
             offsets.data_ptr(), grad.data_ptr() if grad is not None else None,
             _lib.strides4(grad) if grad is not None else None, terms.data_ptr(), N, S, B, C,
             float(l_coord), float(l_noobj), 1.0 / float(batch_size), _COORD_MODES[coord_mode],
-            ws.data_ptr(), ws_bytes, status.data_ptr(), int(variant), _stream_ptr(dev))
+            ws.data_ptr(), ws.numel() * ws.element_size(), status.data_ptr(), int(variant), _stream_ptr(dev))
         _lib.check(rc, "yolo1_loss_fwd_bwd_objects")
     if check and int(status.item()) != 0:
         raise IndexError("yolo_loss_from_objects: a box centre or label lies outside the grid / class range")
