@@ -1,7 +1,7 @@
 """Development aid: decode+NMS throughput of ONE given build of the library (path as argv[1]), for A/B runs of several
 builds inside one gpurun call (box-to-box differences are larger than most code changes):
     for f in tools/_exp/lib_*.so; do python tools/compare_decode_libs.py $f; done
-Prints M images/s for S=7 N=4096 uniform, N=65536 uniform, N=65536 sigmoid, S=14 N=16384 uniform."""
+Prints M images/s for S=7 N=4096 uniform, N=65536 uniform, N=65536 sigmoid, S=14 N=16384 uniform and sigmoid."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,7 +11,8 @@ import yolo_v1_b200 as y
 from yolo_v1_b200 import synth
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 res = []
-for S, N, dist in [(7, 4096, "uniform"), (7, 65536, "uniform"), (7, 65536, "sigmoid"), (14, 16384, "uniform")]:
+for S, N, dist in [(7, 4096, "uniform"), (7, 65536, "uniform"), (7, 65536, "sigmoid"), (14, 16384, "uniform"),
+                   (14, 16384, "sigmoid")]:
     pred = synth.make_decode_inputs(N, S, seed=2, device="cuda", dist=dist)
     M = S * S * 2
     outs = (torch.empty((N, M, 4), device="cuda"), torch.empty((N, M), dtype=torch.int32, device="cuda"),
