@@ -311,6 +311,33 @@ def main():
                 "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": BYTES_PER_CELL * cells, "peak_source": peak_src,
                 "frac_of_nominal_8TBs": achieved / 8000.0}
 
+    # ---------------- the same step through the reference's interface: Module.forward() + loss.backward() -------
+    # (both figures.  YOLOLossV1(...)(pred, target) as train.py:167 calls it, pred a leaf that
+    # requires grad; backward() hands the gradient computed in the forward pass to autograd.)
+    lossLayer = y.YOLOLossV1(N_LOSS, S_LOSS, B, C, 5.0, 0.5, _device=str(dev))
+    pleaf = pred.detach().requires_grad_(True)
+    mod_steps = max(3, min(args.steps, 20))
+
+    def module_step():
+        pleaf.grad = None
+        lossLayer(pleaf, target).backward()
+
+    for _ in range(3):
+        module_step()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    m0.record()
+    for _ in range(mod_steps):
+        module_step()
+    m1.record()
+    torch.cuda.synchronize()
+    mod_ms = m0.elapsed_time(m1) / mod_steps
+    module_autograd = {"value": cells / (mod_ms * 1e-3), "unit": UNIT, "ms_per_step": mod_ms, "steps": mod_steps,
+                       "api": "YOLOLossV1(N, S, B, C, 5, .5)(pred, target).backward() -- v1Loss.py:10,22 / train.py:167,171",
+                       "grad_matches_fused_call": bool(torch.equal(pleaf.grad, grad))}
+    pleaf.grad = None
+    del pleaf
+
     # ---------------- loss: end to end through the host-buffer C ABI ----------------------------------
     e2e = None
     hp = ht = None
@@ -550,7 +577,7 @@ def main():
                    "parallelism": "batch-sharded x%d, one 20-byte NCCL all-reduce of the loss terms per step on a side stream" % world
                    if world > 1 else "single GPU", "timing": "CUDA events on the launch stream, max over ranks"},
         "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "decode_nms": dec, "config1_latency": config1, "parity": parity, "loss": loss_value,
+        "module_autograd": module_autograd, "decode_nms": dec, "config1_latency": config1, "parity": parity, "loss": loss_value,
     }
     print(json.dumps(line), flush=True)
 
