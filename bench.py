@@ -338,6 +338,26 @@ def main():
     pleaf.grad = None
     del pleaf
 
+    # ---------------- stress variant of SURVEY.md 8(d): every second cell holds an object ----------------------
+    # (the object path is ~10x the arithmetic of an empty cell and diverges inside a warp; same tensors otherwise)
+    _, target_s = synth.make_loss_inputs(N_LOSS, S_LOSS, p_obj=0.5, seed=SEED + 3500 + rank, device=dev)
+    for _ in range(3):
+        y.yolo_loss_fused(pred, target_s, batch_size=N_LOSS, out_grad=grad, out_terms=terms, workspace=ws)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s0.record()
+    for _ in range(mod_steps):
+        y.yolo_loss_fused(pred, target_s, batch_size=N_LOSS, out_grad=grad, out_terms=terms, workspace=ws)
+    s1.record()
+    torch.cuda.synchronize()
+    st_ms = s0.elapsed_time(s1) / mod_steps
+    stress = {"workload": "config3 tensors with an object in every second cell (p_obj = 0.5 instead of 3/196)",
+              "value": cells / (st_ms * 1e-3), "unit": UNIT, "ms_per_step": st_ms, "steps": mod_steps,
+              "hbm_gbs": BYTES_PER_CELL * cells / (st_ms * 1e-3) / 1e9,
+              "frac": BYTES_PER_CELL * cells / (st_ms * 1e-3) / 1e9 / hbm_peak}
+    del target_s
+    y.yolo_loss_fused(pred, target, batch_size=N_LOSS, out_grad=grad, out_terms=terms, workspace=ws)   # restore grad
+
     # ---------------- loss: end to end through the host-buffer C ABI ----------------------------------
     e2e = None
     hp = ht = None
@@ -577,7 +597,7 @@ def main():
                    "parallelism": "batch-sharded x%d, one 20-byte NCCL all-reduce of the loss terms per step on a side stream" % world
                    if world > 1 else "single GPU", "timing": "CUDA events on the launch stream, max over ranks"},
         "e2e": e2e, "gpu_launches": args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
-        "module_autograd": module_autograd, "decode_nms": dec, "config1_latency": config1, "parity": parity, "loss": loss_value,
+        "module_autograd": module_autograd, "stress_dense_objects": stress, "decode_nms": dec, "config1_latency": config1, "parity": parity, "loss": loss_value,
     }
     print(json.dumps(line), flush=True)
 
