@@ -164,6 +164,18 @@ def gen_decode(meta):
     # gt=True round trip of an encoder-style target (YOLODataLoader.py:249)
     _, tg = synth.make_loss_inputs(4, 7, seed=13, p_obj=0.15)
     sets["gt_roundtrip_s7"] = (tg, 7, 0.3, 0.5, True)
+    # NaN semantics of the ATen ops the reference runs: torch.max(dim) lets a NaN class score win, so
+    # the slot's score is NaN and `> thresh` drops it; `contain.max()` is NaN as soon as one confidence is, so the
+    # `== max` rule selects nothing.  (NaN only where it cannot reach an emitted box: payload bits are not portable.)
+    nanp = synth.make_tie_free_decode_inputs(4, 7, seed=7)[0].clone()
+    nanp[0, 2, 3, 15] = float("nan")      # class c = 5 of one cell, c = 19 of another, c = 0 of a third
+    nanp[0, 4, 4, 29] = float("nan")
+    nanp[0, 0, 0, 10] = float("nan")
+    nanp[1, 1, 1, 0] = float("nan")       # one NaN confidence among ordinary ones
+    nanp[2, :, :, :2] *= 5e-5             # every confidence <= 1e-4 and one NaN: no candidate at all
+    nanp[2, 5, 2, 1] = float("nan")
+    nanp[3, :, :, :2] *= 5e-5             # the same without the NaN: exactly the maximum is a candidate
+    sets["nan_s7"] = (nanp, 7, 1e-7, 0.5, False)
     for name, (pred, S, th, nth, gt) in sets.items():
         N = pred.shape[0]
         boxes, clss, probs, counts = [], [], [], []
@@ -202,6 +214,17 @@ def gen_decode(meta):
         out[name + "/boxes"], out[name + "/scores"] = bx.numpy(), sc.numpy()
         out[name + "/keep"], out[name + "/thr"] = keep.astype(np.int64), np.float64(thr)
         print("nms case %-20s n=%d thr=%g kept=%d" % (name, n, thr, len(keep)))
+    # NaN scores: torch.sort(descending=True) puts them first (utils/utils.py:161)
+    xy = torch.rand(12, 2, generator=g) * 0.7
+    wh = torch.rand(12, 2, generator=g) * 0.3 + 0.02
+    bx = torch.cat([xy, xy + wh], 1)
+    sc = torch.rand(12, generator=g)
+    sc[3] = sc[7] = float("nan")
+    keep = U.nms(bx, sc, 0.5).numpy()
+    assert np.array_equal(keep, O.nms(bx.numpy(), sc.numpy(), 0.5)) and list(keep[:1]) == [3], keep
+    out["nms_nan_scores/boxes"], out["nms_nan_scores/scores"] = bx.numpy(), sc.numpy()
+    out["nms_nan_scores/keep"], out["nms_nan_scores/thr"] = keep.astype(np.int64), np.float64(0.5)
+    print("nms case %-20s n=12 thr=0.5 kept=%d (NaN scores first)" % ("nms_nan_scores", len(keep)))
     # chain A > B > C: A kills B, B would have killed C, C must survive (iterated suppression)
     bx = torch.tensor([[0.0, 0.0, 1.0, 1.0], [0.45, 0.0, 1.45, 1.0], [0.9, 0.0, 1.9, 1.0], [3, 3, 4, 4.0]])
     sc = torch.tensor([0.9, 0.8, 0.7, 0.6])

@@ -1,8 +1,8 @@
 """Load the REAL reference (haoran1062/YOLO_V1) from /root/reference for golden-vector generation.
 
-TEST INFRASTRUCTURE ONLY.  Used by oracle/make_golden.py in the build container, where the
-read-only reference mount exists.  Nothing on the GPU box (tests -m gpu, smoke(), bench.py) may
-import this module: /root/reference does not exist there.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Used by oracle/make_golden.py in the build container, where the
+read-only reference mount exists, and by bench.py's CPU-reference legs on the GPU box, where only the two
+files staged into oracle/_ref/ exist (oracle/stage_reference.py).  Nothing under yolo_v1_b200/ imports it.
 
 The loss (`v1Loss.py:9-118`) is imported unmodified and built with `_device='cpu'`.
 `utils/utils.py` needs a one-token compatibility shim to run on torch >= 0.5: at
@@ -18,13 +18,41 @@ import sys
 import types
 import warnings
 
-REF_ROOT = os.environ.get("YOLO1_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference_hot_path.zip")
+
+
+def _ref_root():
+    """The reference tree: $YOLO1_REFERENCE_ROOT, else the read-only mount of the build container, else the two
+    hot-path files packed into oracle/_ref/reference_hot_path.zip at build() time by oracle/stage_reference.py
+    (the only form that exists on the GPU box; Python imports from the archive directly)."""
+    env = os.environ.get("YOLO1_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/v1Loss.py"):
+        return "/root/reference"
+    return _STAGED
+
+
+REF_ROOT = _ref_root()
 _SHIM_OLD = "(ovr<=threshold).nonzero().squeeze()"
 _SHIM_NEW = "(ovr<=threshold).nonzero().reshape(-1)"
 
 
+def _is_zip():
+    return os.path.isfile(REF_ROOT) and REF_ROOT.endswith(".zip")
+
+
 def available():
-    return os.path.isfile(os.path.join(REF_ROOT, "v1Loss.py"))
+    return _is_zip() or os.path.isfile(os.path.join(REF_ROOT, "v1Loss.py"))
+
+
+def _read_text(rel):
+    if _is_zip():
+        import zipfile
+        with zipfile.ZipFile(REF_ROOT) as z:
+            return z.read(rel).decode("utf-8")
+    with open(os.path.join(REF_ROOT, rel), "r", encoding="utf-8") as f:
+        return f.read()
 
 
 def load_reference():
@@ -33,8 +61,7 @@ def load_reference():
         raise RuntimeError("reference tree not found at %s" % REF_ROOT)
     sys.dont_write_bytecode = True
     path = os.path.join(REF_ROOT, "utils", "utils.py")
-    with open(path, "r", encoding="utf-8") as f:
-        src = f.read()
+    src = _read_text("utils/utils.py")
     assert src.count(_SHIM_OLD) == 1, "reference nms source changed; shim no longer applies"
     src = src.replace(_SHIM_OLD, _SHIM_NEW)
     # the reference imports `utils.utils`; register the shimmed text under that name so that

@@ -233,9 +233,11 @@ int yolo1_oracle_loss(const float* pred, const int64_t ps[4], const float* targe
  * One image. pred has element strides st[3] over (i,j,channel).  Emits candidates in row-major
  * (i,j,b) order: boxes[k*4..] xyxy, scores[k], cls[k]; returns the count (0 => the caller builds the
  * sentinel of utils/utils.py:134-137).
- *   :108-114 candidate iff conf > fl32(1e-4) or conf == max conf of the image
+ *   :108-114 candidate iff conf > fl32(1e-4) or conf == max conf of the image.  `contain.max()` is ATen's
+ *            NaN-propagating max: one NaN confidence makes it NaN and `contain == max` selects nothing
  *   :121-126 cx = x*cs + j*cs (cs = fl32(1/S)), xyxy = c -/+ 0.5*wh
- *   :127     first arg-max over the C class channels
+ *   :127     first arg-max over the C class channels (torch.max(dim): a NaN class score wins and sticks, so
+ *            the slot's score is NaN and `float(score) > thresh` drops it)
  *   :129     emit iff (double)(conf*maxprob) > thresh   (thresh is a Python double)
  */
 int yolo1_oracle_decode_image(const float* pred, const int64_t st[3], int S, int B, int C, double thresh,
@@ -247,7 +249,7 @@ int yolo1_oracle_decode_image(const float* pred, const int64_t st[3], int S, int
     for (int j = 0; j < S; ++j)
       for (int b = 0; b < B; ++b) {
         float v = pred[i * st[0] + j * st[1] + b * st[2]];
-        if (v > mx) mx = v;
+        if (v > mx || v != v) mx = v; /* NaN sticks: nothing compares greater than it afterwards */
       }
   int k = 0;
   for (int i = 0; i < S; ++i)
@@ -258,7 +260,7 @@ int yolo1_oracle_decode_image(const float* pred, const int64_t st[3], int S, int
       float best_p = C > 0 ? P[(5 * B) * st[2]] : 0.0f;
       for (int c = 1; c < C; ++c) {
         float v = P[(5 * B + c) * st[2]];
-        if (v > best_p) { best_p = v; best_c = c; }
+        if (v > best_p || (v != v && best_p == best_p)) { best_p = v; best_c = c; } /* first NaN wins */
       }
       for (int b = 0; b < B; ++b) {
         float conf = P[b * st[2]];
@@ -290,6 +292,9 @@ int yolo1_oracle_decode_image(const float* pred, const int64_t st[3], int S, int
 typedef struct { float s; int32_t i; } sc_idx;
 static int cmp_desc(const void* a, const void* b) {
   const sc_idx *x = (const sc_idx*)a, *y = (const sc_idx*)b;
+  /* torch.sort(descending=True) orders NaN before every number */
+  const int xn = x->s != x->s, yn = y->s != y->s;
+  if (xn != yn) return xn ? -1 : 1;
   if (x->s > y->s) return -1;
   if (x->s < y->s) return 1;
   return (x->i > y->i) - (x->i < y->i); /* canonical tie order: lower input index first */

@@ -66,6 +66,75 @@ def test_compat_modules_import_like_the_reference():
                 sys.modules[k] = saved[k]
 
 
+_IMPORT_LINES = """
+import sys, types
+sys.dont_write_bytecode = True
+sys.path[:0] = [{compat!r}, {root!r}, {ref!r}]
+for m in ("imgaug", "imgaug.augmenters", "visdom", "torchsummary"):     # third-party packages absent from this image
+    sys.modules.setdefault(m, types.ModuleType(m))
+sys.modules["imgaug"].augmenters = sys.modules["imgaug.augmenters"]
+sys.modules["imgaug"].seed = lambda *a, **k: None
+sys.modules["visdom"].Visdom = object
+# --- train.py:12-14,20 / eval.py:15,17 / run_voc_mAP.py:3, verbatim ---
+from v1Loss import YOLOLossV1
+from utils.YOLODataLoader import yoloDataset
+from utils.utils import *
+from utils.visual import Visual
+# ---
+import yolo_v1_b200 as y
+import utils.utils as uu, utils.YOLODataLoader as dl
+assert YOLOLossV1 is y.YOLOLossV1 and decoder is y.decoder and nms is y.nms and run_test_mAP is y.run_test_mAP
+for name in {helpers!r}:                      # helpers train.py / eval.py use that are NOT on the hot path
+    assert callable(globals()[name]), name
+assert uu._ref is not None and uu._ref.decoder is y.decoder and uu._ref.nms is y.nms   # reference-internal callers
+assert getattr(dl, "decoder", y.decoder) is y.decoder      # a module that star-imports utils.utils gets ours
+assert yoloDataset.__module__ == "utils.YOLODataLoader" and Visual.__module__ == "utils.visual"
+print("ok")
+"""
+
+
+def _run_import_lines(ref_root, helpers):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(y.__file__)))
+    code = _IMPORT_LINES.format(compat=os.path.join(root, "yolo_v1_b200", "compat"), root=root, ref=ref_root,
+                                helpers=tuple(helpers))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_compat_extends_the_reference_utils_package(tmp_path):
+    """with `compat` ahead of the reference on sys.path the shim must EXTEND the reference's `utils`
+    package, not shadow it -- train.py:13 `from utils.YOLODataLoader import yoloDataset`, train.py:20
+    `from utils.visual import Visual` and the non-hot-path helpers of `from utils.utils import *` keep working.
+    Runs train.py's import lines against a stand-in reference tree (same file layout, no __init__.py)."""
+    ref = tmp_path / "ref"
+    (ref / "utils").mkdir(parents=True)
+    (ref / "utils" / "utils.py").write_text(
+        "import os, numpy as np\n"
+        "def decoder(*a, **k):\n    raise AssertionError('the reference decoder must be overridden')\n"
+        "def nms(*a, **k):\n    raise AssertionError('the reference nms must be overridden')\n"
+        "def prep_test_data(file_path, little_test=None):\n    return file_path\n"
+        "def create_logger(base_path, log_name):\n    return None\n"
+        "def cv_resize(img, resize=448):\n    return img\n"
+        "def bbox_un_norm(bboxes, img_size=(448, 448)):\n    return bboxes\n"
+        "def run_test_mAP(*a, **k):\n    return decoder()\n")
+    (ref / "utils" / "YOLODataLoader.py").write_text("from utils.utils import *\nclass yoloDataset:\n    pass\n")
+    (ref / "utils" / "visual.py").write_text("class Visual:\n    pass\n")
+    _run_import_lines(str(ref), ("prep_test_data", "create_logger", "cv_resize", "bbox_un_norm"))
+
+
+def test_compat_against_the_real_reference_tree():
+    """The same import lines against /root/reference itself (build container only)."""
+    import os
+    ref = os.environ.get("YOLO1_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isfile(os.path.join(ref, "utils", "utils.py")):
+        pytest.skip("reference tree not mounted")
+    _run_import_lines(ref, ("prep_test_data", "create_logger", "cv_resize", "bbox_un_norm", "make_eval_tensor",
+                            "from_img_path_get_label_list", "draw_debug_rect"))
+
+
 def test_helper_functions_cpu():
     b1 = torch.tensor([[10., 20., 100., 123.], [200., 300., 300., 350.]])
     b2 = torch.tensor([[50., 60., 150., 120.], [0., 10., 123., 150.], [170., 190., 310., 400.]])

@@ -158,6 +158,19 @@ __device__ __forceinline__ void load_image(const DecodeParams& p, int64_t n, flo
   }
 }
 
+// ATen's max is NaN-propagating (`contain.max()`, utils/utils.py:113; torch.max(dim), :127): FMNMX.NAN, and the
+// warp-wide form as one CREDUX.MAX.F32.NAN (sm_100a `redux.sync` on floats) instead of five shuffle rounds
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float warp_max_nan(float v) {
+  float r;
+  asm volatile("redux.sync.max.NaN.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
+
 // slot index t = cell * B + b, cell = i * S + j, without runtime divisions in the usual case (B = 2; s_magic)
 __device__ __forceinline__ void split_slot(const DecodeParams& p, int t, int& cell, int& b) {
   cell = p.B == 2 ? (t >> 1) : t / p.B;
@@ -190,26 +203,29 @@ __device__ __forceinline__ SlotEval eval_slot(const DecodeParams& p, const Smem&
   int best_c;
   if (PAIRED) {
     // :127 first arg-max.  Lane b = 0 scans classes [0, C/2) starting from the first score like the reference's
-    // scan; lane b = 1 scans [C/2, C) from -inf (a later score only ever wins by `>`, so NaNs are passed over the
-    // same way); the upper half wins only if it is strictly larger.
+    // scan; lane b = 1 scans [C/2, C) from -inf; the upper half wins only if it is strictly larger.  torch.max(dim)
+    // propagates NaN: the value is carried by a NaN-propagating max (a NaN class score makes the slot's score NaN and
+    // `> thresh` drops it, so the index of such a slot is never used); the index follows the `>` of finite scans.
     const int half = (C + 1) >> 1, c0 = b ? half : 1, c1 = b ? C : half;
     best_p = b ? -INFINITY : P[5 * B];
     best_c = b ? half : 0;
     for (int c = c0; c < c1; ++c) {
       const float v = P[5 * B + c];
-      if (v > best_p) best_p = v, best_c = c;
+      if (v > best_p) best_c = c;
+      best_p = fmax_nan(best_p, v);
     }
     const float op = __shfl_xor_sync(0xffffffffu, best_p, 1);
     const int oc = __shfl_xor_sync(0xffffffffu, best_c, 1);
     const float lo_p = b ? op : best_p, hi_p = b ? best_p : op;
     const int lo_c = b ? oc : best_c, hi_c = b ? best_c : oc;
-    best_p = hi_p > lo_p ? hi_p : lo_p;
     best_c = hi_p > lo_p ? hi_c : lo_c;
+    best_p = fmax_nan(hi_p, lo_p);
   } else {
     best_p = P[5 * B], best_c = 0;
     for (int c = 1; c < C; ++c) {
       const float v = P[5 * B + c];
-      if (v > best_p) best_p = v, best_c = c;
+      if (v > best_p) best_c = c;
+      best_p = fmax_nan(best_p, v);
     }
   }
   const float conf = P[b];
@@ -249,9 +265,9 @@ __device__ __forceinline__ int decode_phase_impl(const DecodeParams& p, const Sm
   for (int t = threadIdx.x; t < slots; t += blockDim.x) {
     int cell, b;
     split_slot(p, t, cell, b);
-    mx = fmaxf(mx, sm.img[cell * D + b]);
+    mx = fmax_nan(mx, sm.img[cell * D + b]);   // one NaN confidence: the maximum is NaN and `== max` selects nothing
   }
-  mx = warp_max(mx);
+  mx = warp_max_nan(mx);
   if (lane == 0) red[warp] = mx;
   bool have_mx = false;
 
@@ -272,7 +288,7 @@ __device__ __forceinline__ int decode_phase_impl(const DecodeParams& p, const Sm
     }
     __syncthreads();
     if (!have_mx) {
-      mx = warp_max(lane < nwarps ? red[lane] : -INFINITY);
+      mx = warp_max_nan(lane < nwarps ? red[lane] : -INFINITY);
       have_mx = true;
       if (!(mx > 0.0001f)) continue;   // uniform: this pass again, now with the `== max` rule
     }
@@ -545,7 +561,7 @@ __device__ __forceinline__ int sweep_phase(const Smem& sm, int n, int W) {
 // before the barrier that precedes nms_phase: clear what the phase accumulates into with atomics
 __device__ __forceinline__ void nms_prepare(const Smem& sm, int max_n) {
   if (threadIdx.x == 0) sm.misc[kRankSum] = 0;
-  for (int t = threadIdx.x; t < max_n; t += blockDim.x) sm.sidx[t] = 0;   // NaN scores leave holes: keep them in range
+  for (int t = threadIdx.x; t < max_n; t += blockDim.x) sm.sidx[t] = 0;   // ranks that collide before the tie pass leave holes: keep them in range
 }
 
 template <bool DEFER>
@@ -589,10 +605,14 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
   if (sm.misc[kRankSum] != n * (n - 1) / 2) {   // uniform: equal scores somewhere
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
       const float s = sm.score[k];
+      // NaN scores (stand-alone yolo1_nms only: a decoded NaN score never passes `> thresh`) order before every
+      // number, as torch.sort(descending=True) places them (:161); among themselves by index like any tie
+      const bool s_nan = s != s;
       int rank = 0;
       for (int m = 0; m < n; ++m) {
         const float v = sm.score[m];
-        rank += (v > s) || (v == s && m < k);
+        const bool v_nan = v != v;
+        rank += (v > s) || (v_nan && !s_nan) || ((v == s || (v_nan && s_nan)) && m < k);
       }
       const float4 b = sm.box[k];
       const float ta = p.thr_lo * ((b.z - b.x) * (b.w - b.y));

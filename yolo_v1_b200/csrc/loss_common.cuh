@@ -191,14 +191,20 @@ struct SmemOut<__nv_bfloat16> {
 
 // head epilogue fusion (backbones/OriginResNet.py:186-188: ... bn_end -> torch.sigmoid -> permute): p = sigmoid(z),
 // d loss / d z = d loss / d p * p (1 - p)
-// Branch-free: one MUFU.EX2 and one MUFU.RCP (~3 ulp).  The IEEE forms (expf, 1/x, __frcp_rn) carry a slow-path
-// branch each; 30 of them in a row on the one or two lanes of a warp that hold an object serialise into a
-// dependent chain the rest of the CTA waits for at the tile barrier (measured: 1.22 ms vs 0.72 ms without the head).
+// Branch-free: one MUFU.EX2, one MUFU.RCP and one Newton step on the reciprocal (two FMAs; the result is then
+// within 1 ulp of 1/d, so the only approximation left is ex2's 2 ulp).  The IEEE forms (expf, 1/x, __frcp_rn) carry
+// a slow-path branch each; 30 of them in a row on the one or two lanes of a warp that hold an object serialise into
+// a dependent chain the rest of the CTA waits for at the tile barrier (measured: 1.22 ms vs 0.72 ms without the head).
+// The exponent is clamped to 126 so that d = 1 + 2^t stays finite (d = inf would turn the Newton step into
+// inf * 0 = NaN); sigmoid(z) for z < -87 is then 2^-126 instead of a smaller number -- both are 0 at 1e-5.
+// Error budget: ex2.approx 2^-22 relative, the rounded product z * -log2(e) another |z| 2^-24, the reciprocal
+// 2^-23 -- under 1e-6 for |z| < 10, against the 1e-5 gate of the fused-head tests.
 __device__ __forceinline__ float sigmoid_(float z) {
   float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(z * -1.4426950408889634f, 126.0f)));
+  const float d = 1.0f + e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+  return fmaf(r, fmaf(-d, r, 1.0f), r);
 }
 __device__ __forceinline__ float dsigmoid_(float z) {
   const float pz = sigmoid_(z);

@@ -163,40 +163,62 @@ def _is_dense(t):
     return True
 
 
+_TWICE = ("the fused YOLO loss computed d loss / d pred in forward() and handed that buffer to autograd in the first "
+          "backward(); it cannot be back-propagated a second time.  Construct YOLOLossV1(..., retain_graph=True) to "
+          "keep the buffer (each backward() then returns a fresh, scaled copy), as the reference's autograd graph "
+          "would under loss.backward(retain_graph=True).")
+
+
+def _hand_over(ctx, grad_loss):
+    """backward() of the fused functions.  Default: the stashed gradient is scaled in place (a no-op launch when
+    grad_output == 1, the `loss.backward()` case) and handed to autograd -- zero copies, once.  A second backward()
+    over the same graph raises, as PyTorch does for freed saved tensors.  `retain` mode keeps the stash untouched
+    and returns `stash * grad_output` in a fresh tensor every time (correct for retain_graph=True and for repeated
+    torch.autograd.grad with different grad_outputs; costs one extra pass over the gradient)."""
+    if not ctx.had_grad:
+        return None
+    grad = ctx.grad
+    if grad is None:
+        raise RuntimeError(_TWICE)
+    if ctx.retain:
+        return grad * grad_loss.to(device=grad.device, dtype=grad.dtype)
+    ctx.grad = None
+    if grad.is_cuda:
+        return scale_grad_(grad, grad_loss)
+    # host tensors: the scalar is already on the host, so the no-op test for grad_output == 1 is free
+    if float(grad_loss) != 1.0:
+        grad.mul_(float(grad_loss))
+    return grad
+
+
 class _FusedYoloLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, target, cfg):
+    def forward(ctx, pred, target, cfg, retain):
         need = pred.requires_grad
         loss, grad, terms = yolo_loss_fused(pred.detach(), target, want_grad=need, **cfg)
-        ctx.grad = grad
+        ctx.grad, ctx.had_grad, ctx.retain = grad, need, retain
         ctx.mark_non_differentiable(terms)
         return loss.clone(), terms
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss, _grad_terms):
-        grad = ctx.grad
-        ctx.grad = None
-        if grad is None:
-            return None, None, None
-        return scale_grad_(grad, grad_loss), None, None
+        return _hand_over(ctx, grad_loss), None, None, None
 
 
 class _FusedYoloLossObjects(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, pred, boxes, labels, offsets, cfg):
+    def forward(ctx, pred, boxes, labels, offsets, cfg, retain):
         need = pred.requires_grad
         loss, grad, terms = yolo_loss_from_objects(pred.detach(), boxes, labels, offsets, want_grad=need, **cfg)
-        ctx.grad = grad
+        ctx.grad, ctx.had_grad, ctx.retain = grad, need, retain
         ctx.mark_non_differentiable(terms)
         return loss.clone(), terms
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss, _grad_terms):
-        grad = ctx.grad
-        ctx.grad = None
-        if grad is None:
-            return None, None, None, None, None
-        return scale_grad_(grad, grad_loss), None, None, None, None
+        return _hand_over(ctx, grad_loss), None, None, None, None, None
 
 
 class YOLOLossV1(nn.Module):
@@ -208,14 +230,15 @@ class YOLOLossV1(nn.Module):
         (the reference prints four numbers on every call, v1Loss.py:110, forcing host syncs);
       * keyword-only extras: `coord_mode` ('reference' = the row-slice behaviour of v1Loss.py:101,
         'paper' = xy plain / wh sqrt), `verbose`, `from_logits` (feed the head's pre-sigmoid output; the
-        sigmoid of OriginResNet.py:188 and its backward are fused into the loss kernel).
+        sigmoid of OriginResNet.py:188 and its backward are fused into the loss kernel), `retain_graph`
+        (allow several backward passes over one forward; see `_hand_over`).
     `_device` is accepted for signature compatibility; tensors are used where they live.  Host (CPU)
     tensors are staged through the pipelined host-buffer path of the library (no CPU arithmetic).
     The module has no parameters or buffers (state_dict() of an enclosing model is unchanged).
     """
 
     def __init__(self, _batch_size, _S, _B, _clsN, _l_coord=5., _l_noobj=0.5, _device='cuda:0', _logger=None,
-                 _vis=None, *, coord_mode="reference", verbose=False, from_logits=False):
+                 _vis=None, *, coord_mode="reference", verbose=False, from_logits=False, retain_graph=False):
         super().__init__()
         if coord_mode not in _COORD_MODES:
             raise ValueError("coord_mode must be 'reference' or 'paper'")
@@ -231,6 +254,10 @@ class YOLOLossV1(nn.Module):
         self.coord_mode = coord_mode
         self.verbose = verbose
         self.from_logits = from_logits   # inputs are pre-sigmoid head outputs: sigmoid fused into the kernel
+        # retain_graph=True: backward() may run several times over one forward() (loss.backward(retain_graph=True),
+        # repeated torch.autograd.grad): each call returns stash * grad_output in a fresh tensor.  Default: the stash
+        # is handed over once with no copy and a second backward() raises.
+        self.retain_graph = retain_graph
         self.last_terms = None   # device float32[5] of the latest call (read lazily: no sync unless asked)
         self._host_ctx = None
 
@@ -240,7 +267,7 @@ class YOLOLossV1(nn.Module):
 
     def forward(self, pred_tensor, target_tensor):
         if pred_tensor.is_cuda:
-            loss, terms = _FusedYoloLoss.apply(pred_tensor, target_tensor, self._cfg())
+            loss, terms = _FusedYoloLoss.apply(pred_tensor, target_tensor, self._cfg(), self.retain_graph)
         else:
             loss, terms = self._forward_host(pred_tensor, target_tensor)
         self.last_terms = terms
@@ -252,7 +279,7 @@ class YOLOLossV1(nn.Module):
         """forward(pred, encoder(boxes, labels)) without the dense target: the ragged object lists (CSR, see
         `yolo_v1_b200.pack_objects`) go straight into the kernel.  Additive API; CUDA tensors only."""
         cfg = self._cfg()
-        loss, terms = _FusedYoloLossObjects.apply(pred_tensor, boxes, labels, offsets, cfg)
+        loss, terms = _FusedYoloLossObjects.apply(pred_tensor, boxes, labels, offsets, cfg, self.retain_graph)
         self.last_terms = terms
         if self.logger or self.vis or self.verbose:
             self._report(terms)
@@ -263,7 +290,7 @@ class YOLOLossV1(nn.Module):
             raise RuntimeError("from_logits=True needs CUDA tensors")
         if self._host_ctx is None:
             self._host_ctx = _host.HostContext(self.S, self.B, self.C)
-        return _HostYoloLoss.apply(pred, target, self._host_ctx, self._cfg())
+        return _HostYoloLoss.apply(pred, target, self._host_ctx, self._cfg(), self.retain_graph)
 
     def _report(self, terms):
         t = terms.detach().float().cpu().tolist()   # one sync, only when someone listens
@@ -284,21 +311,15 @@ class _HostYoloLoss(torch.autograd.Function):
     """CPU tensors in, CPU tensors out; the arithmetic still runs on the GPU (pipelined H2D/kernel/D2H)."""
 
     @staticmethod
-    def forward(ctx, pred, target, hctx, cfg):
+    def forward(ctx, pred, target, hctx, cfg, retain):
         need = pred.requires_grad
         terms, grad = hctx.loss(pred.detach(), target, batch_size=cfg["batch_size"], l_coord=cfg["l_coord"],
                                 l_noobj=cfg["l_noobj"], coord_mode=cfg["coord_mode"], want_grad=need)
-        ctx.grad = grad
+        ctx.grad, ctx.had_grad, ctx.retain = grad, need, retain
         ctx.mark_non_differentiable(terms)
         return terms[4].clone(), terms
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_loss, _grad_terms):
-        grad = ctx.grad
-        ctx.grad = None
-        if grad is None:
-            return None, None, None, None
-        # host tensors: the scalar is already on the host, so the no-op test for grad_output == 1 is free
-        if float(grad_loss) != 1.0:
-            grad.mul_(float(grad_loss))
-        return grad, None, None, None
+        return _hand_over(ctx, grad_loss), None, None, None, None

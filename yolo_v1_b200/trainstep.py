@@ -14,7 +14,9 @@ from .loss import YOLOLossV1
 
 __all__ = ["warmming_up_policy", "learning_rate_policy", "ResNet50Yolo", "DenseNet121Yolo", "TrainStep", "LR_ADJUST_MAP"]
 
-LR_ADJUST_MAP = {1: 0.001, 75: 0.0001, 105: 0.00001}    # train.py:46-54 (epoch -> lr)
+# train.py:46-54 (epoch -> lr).  The reference file carries an unresolved merge conflict on the third key: 115 on
+# its HEAD side, 100 on the other; HEAD is taken here.
+LR_ADJUST_MAP = {1: 0.001, 75: 0.0001, 115: 0.00001}
 
 
 def warmming_up_policy(now_iter, now_lr, stop_down_iter=1000):
@@ -97,6 +99,8 @@ class TrainStep:
     def __init__(self, S=7, B=2, C=20, batch_size=16, device="cuda", ddp=False, fuse_head=True, bf16=True,
                  channels_last=True, backbone="resnet50"):
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:      # 'cuda' -> the current device, explicitly
+            self.device = torch.device("cuda", torch.cuda.current_device())
         arch = {"resnet50": ResNet50Yolo, "densenet121": DenseNet121Yolo}[backbone]   # train.py:56-57
         net = arch(S, B, C, return_logits=fuse_head).to(self.device)
         if channels_last:
@@ -105,6 +109,12 @@ class TrainStep:
         self.loss = YOLOLossV1(batch_size, S, B, C, 5., .5, from_logits=fuse_head)
         self.opt = torch.optim.SGD(self.net.parameters(), lr=0.0, momentum=0.99)    # train.py:84
         self.lr, self.iter, self.epoch, self.bf16 = 0.0, 0, 0, bf16
+
+    def start_epoch(self, epoch):
+        """train.py:148 `for epoch in range(num_epochs)`: the lr map is keyed by the epoch number (train.py:158), so
+        the caller's epoch loop reports it here; epoch 0 (the default) is warm-up only, as in the reference."""
+        self.epoch = int(epoch)
+        return self.epoch
 
     def step(self, images, target):
         self.iter += 1
