@@ -38,6 +38,14 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, "r%d.npy" % rank), np.concatenate([mod.last_terms.cpu().numpy(), gterms.cpu().numpy()]))
         np.save(os.path.join(out_dir, "g%d.npy" % rank), p.grad.cpu().numpy())
+        # the same exchange as ONE captured CUDA graph (loss kernel + NCCL all-reduce), replayed twice
+        gl = y.GraphedLoss(b - a, S, 2, 20, average=False)
+        for it in range(2):
+            q = pred[a:b].cuda().requires_grad_(True)
+            gl(q, target[a:b].cuda()).backward()
+        torch.cuda.synchronize()
+        np.save(os.path.join(out_dir, "gr%d.npy" % rank), gl.global_terms.cpu().numpy())
+        np.save(os.path.join(out_dir, "gg%d.npy" % rank), q.grad.cpu().numpy())
     finally:
         dist.destroy_process_group()
 
@@ -62,3 +70,5 @@ def test_two_rank_sharded_loss_over_nccl(tmp_path):
     for r in range(2):
         got = np.load(os.path.join(tmp_path, "r%d.npy" % r))
         assert np.allclose(got[5:], total, rtol=1e-5)
+        assert np.allclose(np.load(os.path.join(tmp_path, "gr%d.npy" % r)), total, rtol=1e-5)      # graph replay
+        assert np.array_equal(np.load(os.path.join(tmp_path, "gg%d.npy" % r)), np.load(os.path.join(tmp_path, "g%d.npy" % r)))

@@ -212,6 +212,122 @@ def test_module_matches_reference_call_shape_and_autograd():
     assert abs(float(l2) - float(o_terms[4])) <= TOL * abs(float(o_terms[4]))
 
 
+@pytest.mark.parametrize("N,S", [(1, 3), (32, 7), (12, 14), (16, 14), (83, 14), (334, 7), (335, 7)])
+def test_small_call_cluster_kernel(N, S):
+    """Calls of up to 16 384 cells run as one 8-CTA cluster launch that settles the `[:2]` rule before it evaluates a
+    cell and uses no workspace (csrc/loss_small.cu): BASELINE config 1 (32 x 7 x 7), train.py:38-41 (12 and 16 images
+    of 14 x 14), the size limit from both sides (334 x 49 = 16 366 cells: cluster kernel; 335 x 49: streaming
+    kernel), every layout / dtype / head form, K = 0..3 objects, and bit-identical agreement with the streaming path's
+    decisions (variant 31 keeps a small call on the streaming kernels)."""
+    y = _y()
+    for p_obj, kind in ((None, "encoder"), (0.3, "mixed")):
+        pred, target = synth.make_loss_inputs(N, S, seed=1000 + N + S, p_obj=p_obj, variant=kind)
+        o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=N)
+        pc, tc = pred.cuda(), target.cuda()
+        ws = torch.full((1 << 17,), 0xAB, dtype=torch.uint8, device="cuda")       # never read by the small kernel
+        _, grad, terms = y.yolo_loss_fused(pc, tc, batch_size=N, workspace=ws)
+        _check(terms, grad, o_terms, o_grad, ("small", N, S, kind))
+        if N * S * S <= 16384:
+            assert bool((ws == 0xAB).all()), "the small-call kernel must not touch the workspace"
+            _, g30, t30 = y.yolo_loss_fused(pc, tc, batch_size=N, variant=30)
+            assert torch.equal(g30, grad) and torch.equal(t30, terms)
+        else:
+            with pytest.raises(RuntimeError):
+                y.yolo_loss_fused(pc, tc, batch_size=N, variant=30)
+        _, g31, t31 = y.yolo_loss_fused(pc, tc, batch_size=N, variant=31)      # the streaming kernel on the same call
+        _check(t31, g31, o_terms, o_grad, ("streaming", N, S, kind))
+        assert torch.allclose(g31, grad, rtol=1e-6, atol=1e-9)
+        # the backbone's permuted NCHW view, forward only, bf16, paper mode
+        planar = pc.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+        _, gp, tp = y.yolo_loss_fused(planar, tc, batch_size=N)
+        assert gp.stride() == planar.stride()
+        _check(tp, gp, o_terms, o_grad, ("small planar", N, S, kind))
+        _, g0, t0 = y.yolo_loss_fused(pc, tc, batch_size=N, want_grad=False)
+        assert g0 is None and torch.equal(t0, terms)
+        op_terms, op_grad = O.loss(pred.numpy(), target.numpy(), batch_size=N, coord_mode=1)
+        _, gq, tq = y.yolo_loss_fused(pc, tc, batch_size=N, coord_mode="paper")
+        _check(tq, gq, op_terms, op_grad, ("small paper", N, S, kind))
+    # K = 0, 1, 2, 3 objects: the first two take the plain form, the third the square-root form
+    pred, _ = synth.make_loss_inputs(N, S, seed=5)
+    cells = [(0, 0, 0), (N - 1, S - 1, S - 1), (N // 2, S // 2, 0)]
+    for K in range(4):
+        target = torch.zeros(N, S, S, 30)
+        for (n, i, j) in sorted(set(cells[:K])):
+            target[n, i, j, :2] = 1.0
+            target[n, i, j, 2:6] = torch.tensor([0.3, 0.6, 0.4, 0.5])
+            target[n, i, j, 6:10] = torch.tensor([0.3, 0.6, 0.4, 0.5])
+            target[n, i, j, 13] = 1.0
+        o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=N)
+        _, grad, terms = y.yolo_loss_fused(pred.cuda(), target.cuda(), batch_size=N)
+        _check(terms, grad, o_terms, o_grad, ("small K", K, N, S))
+
+
+def test_small_call_from_object_lists_and_logits():
+    y = _y()
+    from yolo_v1_b200 import encode as E
+    N, S = 12, 14
+    pred, _ = synth.make_loss_inputs(N, S, seed=9)
+    g = torch.Generator().manual_seed(4)
+    boxes = [torch.rand(3, 4, generator=g) * 0.8 + 0.1 for _ in range(N)]
+    labels = [torch.randint(0, 20, (3,), generator=g) for _ in range(N)]
+    bx, lb, offs = y.pack_objects(boxes, labels)
+    target = y.encode_targets(bx.cuda(), lb.cuda(), offs.cuda(), S)
+    o_terms, o_grad = O.loss(pred.numpy(), target.cpu().numpy(), batch_size=N)
+    _, grad, terms = y.yolo_loss_from_objects(pred.cuda(), bx.cuda(), lb.cuda(), offs.cuda(), batch_size=N)
+    _check(terms, grad, o_terms, o_grad, "small object lists")
+    z = torch.randn(N, S, S, 30, generator=g)
+    p64 = torch.sigmoid(z.double())
+    o_terms, o_grad = O.loss(p64.float().numpy(), target.cpu().numpy(), batch_size=N)
+    want = o_grad.astype(np.float64) * (p64 * (1 - p64)).numpy()
+    _, grad, terms = y.yolo_loss_fused(z.cuda(), target, batch_size=N, from_logits=True)
+    assert np.all(np.abs(terms.cpu().numpy() - o_terms) <= TOL * np.abs(o_terms) + 1e-7)
+    assert np.abs(grad.cpu().numpy() - want).max() <= TOL * np.abs(want).max()
+
+
+def test_graphed_loss_and_allreduce_replay_with_new_inputs():
+    """the loss kernel + the NCCL all-reduce of its terms captured in ONE CUDA graph
+    (yolo_v1_b200/graph.py); replays with new inputs match the oracle.  One GPU: a world-size-1 NCCL group, so the
+    captured graph really holds the collective."""
+    import socket
+    import torch.distributed as dist
+    y = _y()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    started = False
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1,
+                                device_id=torch.device("cuda", 0))
+        started = True
+    try:
+        N, S = 12, 14                                   # train.py:38-41
+        g = y.GraphedLoss(N, S, 2, 20)
+        for it in range(4):
+            pred, target = synth.make_loss_inputs(N, S, seed=300 + it, p_obj=0.05)
+            o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=N)
+            p = pred.cuda().requires_grad_(True)
+            loss = g(p, target.cuda())
+            assert loss.grad_fn is not None
+            loss.backward()
+            _check(g.global_terms, p.grad, o_terms, o_grad, ("graphed", it))
+            assert abs(float(loss) - float(o_terms[4])) <= TOL * abs(float(o_terms[4]))
+        assert g.graph is not None and g.serial == 4
+        # the permuted NCHW view with bf16 logits (what the backbone hands over in config 5) needs its own capture
+        g2 = y.GraphedLoss(N, S, 2, 20, from_logits=True)
+        z = (torch.randn(N, 30, S, S, generator=torch.Generator().manual_seed(1)) * 1.5).to(torch.bfloat16)
+        _, target = synth.make_loss_inputs(N, S, seed=77, p_obj=0.05)
+        zv = z.cuda().permute(0, 2, 3, 1).requires_grad_(True)
+        g2(zv, target.cuda()).backward()
+        _, want_g, want_t = y.yolo_loss_fused(zv.detach(), target.cuda(), batch_size=N, from_logits=True)
+        assert torch.equal(g2.global_terms, want_t) and torch.equal(zv.grad, want_g)
+        with pytest.raises(ValueError):
+            g2(zv.detach().contiguous(), target.cuda())
+    finally:
+        if started:
+            dist.destroy_process_group()
+
+
 def test_second_backward_raises_and_retain_graph_mode():
     """The reference's autograd graph (v1Loss.py:22-118) can be back-propagated again under retain_graph=True and
     accumulates; without it PyTorch raises.  The fused module hands its gradient buffer over once: a second

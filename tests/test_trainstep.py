@@ -51,3 +51,59 @@ def test_one_bf16_train_step_updates_the_network():
         assert l0 == l0 and l1 == l1 and l0 > 0          # finite
         assert not torch.equal(w0, ts.net.layer6.weight)   # the gradient reached the head through the fused loss
         assert ts.lr == 0.001
+
+
+@pytest.mark.gpu
+def test_train_step_equals_the_reference_step_with_the_stock_loss():
+    """train.py:163-172 on a fixed seed: lr policy -> forward -> loss -> zero_grad -> backward -> SGD(momentum 0.99).
+    Two copies of the same network take two steps on the same batches: one through TrainStep (fused CUDA loss, eager
+    and graph-captured), the other through the reference's step order with the STOCK loss swapped in -- the unmodified
+    `YOLOLossV1` of v1Loss.py on CPU (oracle/_ref, when staged) or the C oracle pinned to it, whose gradient with
+    respect to the network output is handed to the same backbone.  All parameters must agree after the steps."""
+    import copy
+    import numpy as np
+    from oracle import oracle as O
+    from oracle import ref_loader
+    S, N = 7, 4
+    ref_mod = None
+    if ref_loader.available():
+        RefLoss, _ = ref_loader.load_reference()
+        ref_mod = RefLoss(N, S, 2, 20, 5., .5, _device='cpu')
+    for graph in (False, True):
+        torch.manual_seed(0)
+        ts = TrainStep(S=S, batch_size=N, device="cuda:0", fuse_head=False, bf16=False, channels_last=False,
+                       backbone="resnet50", graph_loss=graph)
+        twin = copy.deepcopy(ts.net)                     # train mode on both: the same batch statistics, as train.py runs
+        opt = torch.optim.SGD(twin.parameters(), lr=0.0, momentum=0.99)                 # train.py:84
+        lr, it = 0.0, 0
+        ts.start_epoch(1)                                # epoch 1 -> lr 1e-3 (train.py:46-54)
+        for step in range(2):
+            images = torch.randn(N, 3, 448, 448, generator=torch.Generator().manual_seed(10 + step)).cuda()
+            _, target = synth.make_loss_inputs(N, S, seed=20 + step, p_obj=0.1)
+            l_ours = float(ts.step(images, target.cuda()))
+            # the reference step (train.py:157-172) with the stock loss
+            it += 1
+            lr = learning_rate_policy(it, 1, lr, LR_ADJUST_MAP)
+            for g in opt.param_groups:
+                g["lr"] = lr
+            pred = twin(images)
+            if ref_mod is not None:
+                pc = pred.detach().cpu().contiguous().requires_grad_(True)
+                with ref_loader.quiet():
+                    l_ref = ref_mod(pc, target)
+                    l_ref.backward()
+                l_ref, g_ref = float(l_ref), pc.grad
+            else:
+                t5, g_np = O.loss(pred.detach().cpu().contiguous().numpy(), target.numpy(), batch_size=N)
+                l_ref, g_ref = float(t5[4]), torch.from_numpy(g_np)
+            opt.zero_grad()
+            pred.backward(g_ref.cuda())
+            opt.step()
+            assert abs(l_ours - l_ref) <= 1e-5 * abs(l_ref), (graph, step, l_ours, l_ref)
+        assert ts.lr == lr == 0.001
+        worst = 0.0
+        for (n1, p1), (n2, p2) in zip(ts.net.named_parameters(), twin.named_parameters()):
+            d = float((p1 - p2).abs().max())
+            scale = float(p2.abs().max()) + 1e-12
+            worst = max(worst, d / scale)
+        assert worst <= 2e-5, (graph, worst)

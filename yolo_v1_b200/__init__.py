@@ -12,5 +12,6 @@ from .voc import voc_eval, voc_ap, run_test_mAP, detections_to_voc_preds, boxes_
 from .encode import encode_targets, encoder, pack_objects             # noqa: F401
 from .host import HostContext                                        # noqa: F401
 from .dist import shard_range, all_reduce_terms, sharded_loss        # noqa: F401
+from .graph import GraphedLoss                                       # noqa: F401
 
 __version__ = "0.1.0"

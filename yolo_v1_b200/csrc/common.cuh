@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "../../include/yolo1_b200.h"
 
 namespace yolo1 {
@@ -19,6 +21,54 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
     cudaError_t _e = (expr);                      \
     if (_e != cudaSuccess) return (int)_e;        \
   } while (0)
+
+// ---- launch hygiene: per (kernel, device) one-time work ---------------------------------------------------
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), cudaDeviceGetAttribute(MultiProcessorCount) and
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor are driver round trips of a few microseconds each; a small call
+// (train.py:38-41: 2 352 cells) is shorter than the three together.  Each launcher owns one `static KernelPrep`
+// (so: one per kernel instantiation) and asks it; the driver is consulted only when the device, the block size
+// or the shared-memory size differ from what was seen last.
+constexpr int kMaxDevices = 64;
+struct KernelPrep {
+  std::mutex mu;
+  size_t attr_smem[kMaxDevices] = {};   // largest dynamic shared-memory size the kernel was opted in for
+  int sms[kMaxDevices] = {};
+  int occ_threads[kMaxDevices] = {};
+  size_t occ_smem[kMaxDevices] = {};
+  int per_sm[kMaxDevices] = {};
+  bool occ_valid[kMaxDevices] = {};
+};
+// Returns 0 and fills sms / per_sm (resident CTAs per SM, >= 1; pass want_occupancy = false to skip the query).
+template <typename K>
+int prepare_kernel(KernelPrep& c, K kern, int threads, size_t smem, bool want_occupancy, int* sms, int* per_sm) {
+  int dev = 0;
+  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
+  const int d = (dev >= 0 && dev < kMaxDevices) ? dev : -1;
+  std::lock_guard<std::mutex> lock(c.mu);
+  if (d < 0 || smem > c.attr_smem[d]) {
+    if (smem > 48 * 1024 || d < 0)
+      YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (d >= 0) c.attr_smem[d] = smem;
+  }
+  int n_sm = d >= 0 ? c.sms[d] : 0;
+  if (n_sm == 0) {
+    YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    if (d >= 0) c.sms[d] = n_sm;
+  }
+  if (sms) *sms = n_sm;
+  if (want_occupancy) {
+    int occ = 1;
+    if (d >= 0 && c.occ_valid[d] && c.occ_threads[d] == threads && c.occ_smem[d] == smem) {
+      occ = c.per_sm[d];
+    } else {
+      YOLO1_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+      if (occ < 1) occ = 1;
+      if (d >= 0) c.occ_valid[d] = true, c.occ_threads[d] = threads, c.occ_smem[d] = smem, c.per_sm[d] = occ;
+    }
+    if (per_sm) *per_sm = occ;
+  }
+  return 0;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

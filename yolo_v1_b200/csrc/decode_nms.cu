@@ -751,13 +751,15 @@ __global__ void __launch_bounds__(256) boxes_to_pixels_kernel(const float4* __re
 // three full warps; 128: -4 %, 160: -13 %, 256: -27 %), 384 for 14x14 (256: -3 %, 512: -3 %)
 int block_threads(int max_n) { return max_n <= 128 ? 96 : (max_n <= 256 ? 256 : 384); }
 
-template <typename K>
-int launch(K kern, const DecodeParams& p, int64_t N, int img_floats, cudaStream_t stream) {
+// KERN is a template VALUE parameter, so every kernel gets its own static KernelPrep (the kernels share one type)
+template <auto KERN>
+int launch(const DecodeParams& p, int64_t N, int img_floats, cudaStream_t stream) {
   if (N == 0) return 0;
   const size_t smem = smem_layout(nullptr, img_floats, p.max_n, nullptr);
   if (smem > 227 * 1024) return YOLO1_ERR_UNSUPPORTED;
-  YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)N, block_threads(p.max_n), smem, stream>>>(p);
+  static KernelPrep prep;
+  if (int rc = prepare_kernel(prep, KERN, block_threads(p.max_n), smem, false, nullptr, nullptr)) return rc;
+  KERN<<<(unsigned)N, block_threads(p.max_n), smem, stream>>>(p);
   return (int)cudaGetLastError();
 }
 
@@ -822,8 +824,8 @@ int yolo1_decode(const void* pred, const int64_t pred_strides[4], int pred_dtype
   fill_decode(p, pred, pred_strides, S, B, C, thresh);
   p.boxes = boxes, p.scores = scores, p.cls = cls, p.counts = counts;
   const int img = S * S * (5 * B + C);
-  if (pred_dtype == YOLO1_DTYPE_BF16) return launch(decode_kernel<__nv_bfloat16>, p, N, img, (cudaStream_t)stream);
-  return launch(decode_kernel<float>, p, N, img, (cudaStream_t)stream);
+  if (pred_dtype == YOLO1_DTYPE_BF16) return launch<decode_kernel<__nv_bfloat16>>(p, N, img, (cudaStream_t)stream);
+  return launch<decode_kernel<float>>(p, N, img, (cudaStream_t)stream);
 }
 
 int yolo1_nms(const float* boxes, const float* scores, const int32_t* cls, const int32_t* counts, int64_t N,
@@ -843,8 +845,8 @@ int yolo1_nms(const float* boxes, const float* scores, const int32_t* cls, const
   p.keep = keep, p.out_counts = keep_counts;
   p.max_n = max_n, p.per_class = per_class ? 1 : 0;
   set_threshold(p, iou_thr);
-  if (max_n <= 128) return launch(nms_kernel<true>, p, N, 0, (cudaStream_t)stream);
-  return launch(nms_kernel<false>, p, N, 0, (cudaStream_t)stream);
+  if (max_n <= 128) return launch<nms_kernel<true>>(p, N, 0, (cudaStream_t)stream);
+  return launch<nms_kernel<false>>(p, N, 0, (cudaStream_t)stream);
 }
 
 int yolo1_boxes_to_pixels(const float* boxes, int64_t n_boxes, float img_w, float img_h, int32_t* pixels,
@@ -882,10 +884,10 @@ int yolo1_decode_nms(const void* pred, const int64_t pred_strides[4], int pred_d
   const int img = S * S * (5 * B + C);
   const bool defer = p.max_n <= 128;   // see nms_row
   if (pred_dtype == YOLO1_DTYPE_BF16)
-    return defer ? launch(decode_nms_kernel<__nv_bfloat16, true>, p, N, img, (cudaStream_t)stream)
-                 : launch(decode_nms_kernel<__nv_bfloat16, false>, p, N, img, (cudaStream_t)stream);
-  return defer ? launch(decode_nms_kernel<float, true>, p, N, img, (cudaStream_t)stream)
-               : launch(decode_nms_kernel<float, false>, p, N, img, (cudaStream_t)stream);
+    return defer ? launch<decode_nms_kernel<__nv_bfloat16, true>>(p, N, img, (cudaStream_t)stream)
+                 : launch<decode_nms_kernel<__nv_bfloat16, false>>(p, N, img, (cudaStream_t)stream);
+  return defer ? launch<decode_nms_kernel<float, true>>(p, N, img, (cudaStream_t)stream)
+               : launch<decode_nms_kernel<float, false>>(p, N, img, (cudaStream_t)stream);
 }
 
 }  // extern "C"

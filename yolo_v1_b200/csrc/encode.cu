@@ -111,12 +111,9 @@ extern "C" YOLO1_API int yolo1_encode_targets(const float* boxes, const int32_t*
   if (G > 1 && (G & 1)) G -= 1;  // an even image count keeps every tile a multiple of 16 bytes
   p.G = G;
   const size_t smem = (size_t)G * img_bytes;
-  YOLO1_CUDA_TRY(cudaFuncSetAttribute(encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = kNumSMs, per_sm = 1;
-  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
-  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  YOLO1_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_kernel, 256, smem));
-  if (per_sm < 1) per_sm = 1;
+  static yolo1::KernelPrep prep;
+  int sms = kNumSMs, per_sm = 1;
+  if (int rc = yolo1::prepare_kernel(prep, encode_kernel, 256, smem, true, &sms, &per_sm)) return rc;
   if (per_sm > 8) per_sm = 8;
   int64_t grid = (N + G - 1) / G;
   if (grid > (int64_t)sms * per_sm) grid = (int64_t)sms * per_sm;   // every CTA resident: the loop is grid-strided

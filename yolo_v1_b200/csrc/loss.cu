@@ -183,9 +183,9 @@ int launch_hostmapped(const LossParams& p, cudaStream_t stream) {
   constexpr int TILE = 128;
   constexpr size_t smem = 2 * TILE * 30 * sizeof(float);
   auto kern = loss_hostmapped_kernel<HAS_GRAD, TILE>;
-  int dev = 0, sms = kNumSMs;
-  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
-  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static KernelPrep prep;
+  int sms = kNumSMs;
+  if (int rc = prepare_kernel(prep, kern, TILE, smem, false, &sms, nullptr)) return rc;
   const int64_t tiles = p.cells / TILE;
   int64_t grid = (int64_t)sms * 6;   // 31 KB and 128 threads per CTA: plenty of PCIe requests in flight
   if (grid > tiles) grid = tiles;
@@ -197,9 +197,9 @@ int launch_hostmapped(const LossParams& p, cudaStream_t stream) {
 
 template <typename E, bool HAS_GRAD>
 int launch_generic(const LossParams& p, cudaStream_t stream) {
-  int dev = 0, sms = kNumSMs;
-  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
-  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static KernelPrep prep;
+  int sms = kNumSMs;
+  if (int rc = prepare_kernel(prep, loss_generic_kernel<E, HAS_GRAD>, kGenericThreads, 0, false, &sms, nullptr)) return rc;
   int64_t grid = (p.cells + kGenericThreads - 1) / kGenericThreads;
   const int64_t cap = (int64_t)sms * 8;
   if (grid > cap) grid = cap;
@@ -254,6 +254,14 @@ int loss_launch_chunk_impl(const void* pred, const int64_t ps[4], int pred_dtype
   p.cellobj = lists ? lists->cellobj : nullptr, p.boxes = lists ? lists->boxes : nullptr;
   p.labels = lists ? lists->labels : nullptr, p.cs = (float)(1.0 / (double)S);
   if (lists) p.target = nullptr;
+
+  // Small single-chunk calls (train.py:38-41 trains with 12 x 14 x 14 = 2 352 cells; BASELINE config 1 is 1 568):
+  // one cluster, no workspace to reset, no fix-up pass (loss_small.cu).
+  const bool one_chunk = (chunk_flags & 3) == 3;
+  if (variant == kVariantSmall && !(one_chunk && cells > 0 && cells <= loss_small_max_cells())) return YOLO1_ERR_UNSUPPORTED;
+  if (one_chunk && cells > 0 && cells <= loss_small_max_cells() && (variant == 0 || variant == kVariantSmall))
+    return launch_loss_small(p, pred_dtype == YOLO1_DTYPE_BF16, grad != nullptr, stream);
+  if (variant == kVariantNoSmall) variant = 0;
 
   if (chunk_flags & 1) YOLO1_CUDA_TRY(cudaMemsetAsync(workspace, 0, offsetof(LossWs, partial), stream));
 
@@ -339,7 +347,8 @@ int yolo1_loss_fwd_bwd_objects_ex(const void* pred, const int64_t pred_strides[4
     G = G < 4 ? 4 : (G > 256 ? 256 : (G & ~3));   // a multiple of 4 images keeps every CTA's slice 16-byte aligned
     const size_t smem = (size_t)G * S * S * sizeof(int32_t);
     if (smem > 200 * 1024) return YOLO1_ERR_UNSUPPORTED;
-    YOLO1_CUDA_TRY(cudaFuncSetAttribute(object_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static KernelPrep prep;
+    if (int rc = prepare_kernel(prep, object_cells_kernel, 256, smem, false, nullptr, nullptr)) return rc;
     object_cells_kernel<<<(unsigned)((N + G - 1) / G), 256, smem, s>>>(boxes, labels, offsets, N, S, C,
                                                                       (float)(1.0 / (double)S), G, cellobj, status);
     YOLO1_CUDA_TRY(cudaGetLastError());

@@ -77,6 +77,11 @@ int planar_tile_imgs(int S, size_t esz, int target_cells, bool list_mode);
 // warp-specialised form (loss_ws.cu): tile_cells cells per tile, stages 2 or 3, gradient tile in place
 int launch_loss_ws(const LossParams& p, bool bf16, bool has_grad, bool is_planar, int tile_cells, int stages,
                    cudaStream_t stream);
+// small calls (loss_small.cu): one cluster, no workspace; any layout / (B, C) / dtype
+int64_t loss_small_max_cells();
+int launch_loss_small(const LossParams& p, bool bf16, bool has_grad, cudaStream_t stream);
+constexpr int kVariantSmall = 30;   // yolo1_loss_fwd_bwd_ex: force the small-call kernel (error when too large)
+constexpr int kVariantNoSmall = 31; // ... or keep a small call on the streaming kernels (A/B measurements)
 
 namespace {
 
@@ -433,9 +438,11 @@ __device__ __forceinline__ bool cell_b2c20(const PA& P, const TA& T, const GA& G
 // call's first two object cells: writes only the 4 coordinate gradients of the responsible box in plain
 // form and returns (plain - sqrt) of the location sum in s.loc.
 // ZEROED = true: the gradient row was already cleared (cooperative vector stores), skip the zero stores.
+// plain = true (small-call kernel, loss_small.cu): the caller already knows that this is one of the call's first two
+// object cells, so the cell is evaluated in plain form right away and no fix-up follows.
 template <bool HAS_GRAD, bool FIX, bool ZEROED = false, typename PA, typename TA, typename GA>
 __device__ __forceinline__ bool cell_generic(const PA& P, const TA& T, const GA& G, const LossParams& k,
-                                             CellSums& s) {
+                                             CellSums& s, bool plain = false) {
   const int B = k.B, C = k.C, D = 5 * B + C;
   if (T.ld(0) != 1.0f) {
     if (!FIX) {
@@ -498,7 +505,7 @@ __device__ __forceinline__ bool cell_generic(const PA& P, const TA& T, const GA&
 #pragma unroll
   for (int d = 0; d < 4; ++d) {
     const float g = T.ld(B + 4 * r + d);
-    const float gl = coord_term(pr[d], g, FIX || (paper && d < 2), loc);
+    const float gl = coord_term(pr[d], g, FIX || plain || (paper && d < 2), loc);
     if (FIX) (void)coord_term(pr[d], g, false, loc_sqrt);
     if (HAS_GRAD) G.st(B + 4 * r + d, (k.lc * gl - 2.0f * dconf * dI[d]) * k.inv_bs);
   }

@@ -120,12 +120,9 @@ int launch_tma(const LossParams& p, cudaStream_t stream) {
   constexpr size_t smem = (size_t)STAGES * TILE * (30 * sizeof(E) + (LIST ? 4 : 120)) +
                           (size_t)NOUT * TILE * 30 * sizeof(E) + STAGES * sizeof(uint64_t);
   auto kern = loss_tma_kernel<E, HAS_GRAD, TILE, STAGES, NOUT, SIG, LIST>;
-  YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = kNumSMs, per_sm = 1;
-  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
-  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  YOLO1_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TILE, smem));
-  if (per_sm < 1) per_sm = 1;
+  static KernelPrep prep;   // one per kernel instantiation: attribute / occupancy queries once per device
+  int sms = kNumSMs, per_sm = 1;
+  if (int rc = prepare_kernel(prep, kern, TILE, smem, true, &sms, &per_sm)) return rc;
   const int64_t tiles = p.cells / TILE;
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > tiles) grid = tiles;
@@ -241,12 +238,9 @@ int launch_tma_any(const LossParams& p, cudaStream_t stream) {
   const size_t smem = (size_t)tile * D * (4 * sizeof(E) + 8) + 2 * sizeof(uint64_t);
   if (smem > 200 * 1024) return YOLO1_ERR_UNSUPPORTED;
   auto kern = loss_tma_any_kernel<E, HAS_GRAD>;
-  YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = kNumSMs, per_sm = 1;
-  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
-  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  YOLO1_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tile, smem));
-  if (per_sm < 1) per_sm = 1;
+  static KernelPrep prep;
+  int sms = kNumSMs, per_sm = 1;
+  if (int rc = prepare_kernel(prep, kern, tile, smem, true, &sms, &per_sm)) return rc;
   const int64_t tiles = p.cells / tile;
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > tiles) grid = tiles;

@@ -127,12 +127,9 @@ int launch_planar_n(const LossParams& p, int tile_imgs, cudaStream_t stream) {
                       (size_t)NOUT * tile_cells * 30 * sizeof(E) + STAGES * sizeof(uint64_t);
   const int threads = (tile_cells + 31) / 32 * 32;
   auto kern = loss_tma_planar_kernel<E, HAS_GRAD, STAGES, NOUT, SIG, LIST>;
-  YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = kNumSMs, per_sm = 1;
-  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
-  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  YOLO1_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-  if (per_sm < 1) per_sm = 1;
+  static KernelPrep prep;   // one per kernel instantiation: attribute / occupancy queries once per device
+  int sms = kNumSMs, per_sm = 1;
+  if (int rc = prepare_kernel(prep, kern, threads, smem, true, &sms, &per_sm)) return rc;
   const int64_t tiles = p.cells / tile_cells;
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > tiles) grid = tiles;

@@ -139,12 +139,9 @@ int launch_ws_t(const LossParams& p, int tile_cells, cudaStream_t stream) {
   const int threads = (tile_cells + 31) / 32 * 32 + 32;
   if (threads > 288 || smem > 227 * 1024) return YOLO1_ERR_UNSUPPORTED;
   auto kern = loss_ws_kernel<E, HAS_GRAD, PLANAR, STAGES, SIG, LIST>;
-  YOLO1_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = kNumSMs, per_sm = 1;
-  YOLO1_CUDA_TRY(cudaGetDevice(&dev));
-  YOLO1_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  YOLO1_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
-  if (per_sm < 1) per_sm = 1;
+  static KernelPrep prep;   // one per kernel instantiation: attribute / occupancy queries once per device
+  int sms = kNumSMs, per_sm = 1;
+  if (int rc = prepare_kernel(prep, kern, threads, smem, true, &sms, &per_sm)) return rc;
   const int64_t tiles = p.cells / tile_cells;
   int64_t grid = (int64_t)sms * per_sm;
   if (grid > tiles) grid = tiles;

@@ -10,6 +10,7 @@ kernel can be measured inside a real bf16 DDP step.  The head's sigmoid + permut
 import torch
 import torch.nn as nn
 
+from .graph import GraphedLoss
 from .loss import YOLOLossV1
 
 __all__ = ["warmming_up_policy", "learning_rate_policy", "ResNet50Yolo", "DenseNet121Yolo", "TrainStep", "LR_ADJUST_MAP"]
@@ -97,7 +98,7 @@ class TrainStep:
     bf16 autocast and DistributedDataParallel are the B200 additions (config 5)."""
 
     def __init__(self, S=7, B=2, C=20, batch_size=16, device="cuda", ddp=False, fuse_head=True, bf16=True,
-                 channels_last=True, backbone="resnet50"):
+                 channels_last=True, backbone="resnet50", graph_loss=False):
         self.device = torch.device(device)
         if self.device.type == "cuda" and self.device.index is None:      # 'cuda' -> the current device, explicitly
             self.device = torch.device("cuda", torch.cuda.current_device())
@@ -107,6 +108,9 @@ class TrainStep:
             net = net.to(memory_format=torch.channels_last)
         self.net = nn.parallel.DistributedDataParallel(net, device_ids=[self.device.index]) if ddp else net
         self.loss = YOLOLossV1(batch_size, S, B, C, 5., .5, from_logits=fuse_head)
+        # graph_loss: the loss kernel + the all-reduce of its terms vector (job-wide logging under DDP) replayed as one
+        # CUDA graph (yolo_v1_b200/graph.py) instead of eager launches -- SURVEY 8(f) row 4
+        self.graphed = GraphedLoss(batch_size, S, B, C, 5., .5, from_logits=fuse_head) if graph_loss else None
         self.opt = torch.optim.SGD(self.net.parameters(), lr=0.0, momentum=0.99)    # train.py:84
         self.lr, self.iter, self.epoch, self.bf16 = 0.0, 0, 0, bf16
 
@@ -123,7 +127,10 @@ class TrainStep:
             g["lr"] = self.lr
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.bf16):
             pred = self.net(images)
-        loss = self.loss(pred, target)        # bf16 or fp32 logits, permuted NCHW view, read in place
+        if self.graphed is not None:
+            loss = self.graphed(pred, target)  # one graph launch: loss kernel + NCCL all-reduce of the terms
+        else:
+            loss = self.loss(pred, target)    # bf16 or fp32 logits, permuted NCHW view, read in place
         self.opt.zero_grad(set_to_none=True)
         loss.backward()
         self.opt.step()
