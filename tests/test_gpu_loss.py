@@ -17,7 +17,8 @@ from yolo_v1_b200 import synth
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-5
-VARIANTS = [0, 1, 2, 3, 5, 8, 13, -1]   # launch shapes of the streaming kernel; -1 = strided kernel
+VARIANTS = [0, 1, 2, 3, 5, 8, 13, -1, 31, 40, 41, 42]   # launch shapes of the streaming kernel; -1 = strided kernel;
+# 31 = streaming default shape even for a small call; 40-42 = confidence-first sector-read kernel (loss_sparse.cu)
 
 
 def _y():
@@ -212,23 +213,24 @@ def test_module_matches_reference_call_shape_and_autograd():
     assert abs(float(l2) - float(o_terms[4])) <= TOL * abs(float(o_terms[4]))
 
 
-@pytest.mark.parametrize("N,S", [(1, 3), (32, 7), (12, 14), (16, 14), (83, 14), (334, 7), (335, 7)])
+@pytest.mark.parametrize("N,S", [(1, 3), (1, 7), (32, 7), (12, 14), (16, 14), (36, 14), (150, 7), (128, 14)])
 def test_small_call_cluster_kernel(N, S):
-    """Calls of up to 16 384 cells run as one 8-CTA cluster launch that settles the `[:2]` rule before it evaluates a
-    cell and uses no workspace (csrc/loss_small.cu): BASELINE config 1 (32 x 7 x 7), train.py:38-41 (12 and 16 images
-    of 14 x 14), the size limit from both sides (334 x 49 = 16 366 cells: cluster kernel; 335 x 49: streaming
-    kernel), every layout / dtype / head form, K = 0..3 objects, and bit-identical agreement with the streaming path's
-    decisions (variant 31 keeps a small call on the streaming kernels)."""
+    """Small calls run as ONE 8-CTA cluster launch that settles the `[:2]` rule before it evaluates a cell and uses no
+    workspace (csrc/loss_small.cu): BASELINE config 1 (32 x 7 x 7), train.py:38-41 (12 and 16 images of 14 x 14), an
+    odd cell count (generic form), the resident form near its capacity (36 x 196 = 7 056 and 150 x 49 = 7 350 of
+    7 360 cells for fp32 NHWC) and a call beyond it (128 x 196: streaming kernels), every layout / dtype / head form,
+    K = 0..3 objects, and agreement with the streaming path (variant 31 keeps a small call on the streaming kernels)."""
     y = _y()
+    cells = N * S * S
     for p_obj, kind in ((None, "encoder"), (0.3, "mixed")):
         pred, target = synth.make_loss_inputs(N, S, seed=1000 + N + S, p_obj=p_obj, variant=kind)
         o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=N)
         pc, tc = pred.cuda(), target.cuda()
-        ws = torch.full((1 << 17,), 0xAB, dtype=torch.uint8, device="cuda")       # never read by the small kernel
+        ws = torch.full((1 << 17,), 0xAB, dtype=torch.uint8, device="cuda")       # never read by the small kernels
         _, grad, terms = y.yolo_loss_fused(pc, tc, batch_size=N, workspace=ws)
         _check(terms, grad, o_terms, o_grad, ("small", N, S, kind))
-        if N * S * S <= 16384:
-            assert bool((ws == 0xAB).all()), "the small-call kernel must not touch the workspace"
+        if cells <= 7360:
+            assert bool((ws == 0xAB).all()), "the small-call kernels must not touch the workspace"
             _, g30, t30 = y.yolo_loss_fused(pc, tc, batch_size=N, variant=30)
             assert torch.equal(g30, grad) and torch.equal(t30, terms)
         else:
@@ -242,6 +244,12 @@ def test_small_call_cluster_kernel(N, S):
         _, gp, tp = y.yolo_loss_fused(planar, tc, batch_size=N)
         assert gp.stride() == planar.stride()
         _check(tp, gp, o_terms, o_grad, ("small planar", N, S, kind))
+        pb = pred.to(torch.bfloat16)
+        ob_terms, ob_grad = O.loss(pb.float().numpy(), target.numpy(), batch_size=N)
+        for view in (pb.cuda(), pb.cuda().permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)):
+            _, gb, tb = y.yolo_loss_fused(view, tc, batch_size=N)
+            _check(tb, None, ob_terms, None, ("small bf16", N, S, kind))
+            assert np.all(np.abs(gb.float().cpu().numpy() - ob_grad) <= np.abs(ob_grad) * 2.0 ** -8 + 1e-30)
         _, g0, t0 = y.yolo_loss_fused(pc, tc, batch_size=N, want_grad=False)
         assert g0 is None and torch.equal(t0, terms)
         op_terms, op_grad = O.loss(pred.numpy(), target.numpy(), batch_size=N, coord_mode=1)

@@ -74,16 +74,20 @@ def test_train_step_equals_the_reference_step_with_the_stock_loss():
         ts = TrainStep(S=S, batch_size=N, device="cuda:0", fuse_head=False, bf16=False, channels_last=False,
                        backbone="resnet50", graph_loss=graph)
         twin = copy.deepcopy(ts.net)                     # train mode on both: the same batch statistics, as train.py runs
+        init = [q.detach().clone() for q in ts.net.parameters()]
         opt = torch.optim.SGD(twin.parameters(), lr=0.0, momentum=0.99)                 # train.py:84
         lr, it = 0.0, 0
-        ts.start_epoch(1)                                # epoch 1 -> lr 1e-3 (train.py:46-54)
-        for step in range(2):
+        # epoch 0 = the warm-up ramp of train.py:22-25 (lr 1e-6, 2e-6, ...): a randomly initialised network is only
+        # comparable step for step while the update stays in the linear regime (at lr 1e-3 a 1e-7 difference in the
+        # gradient moves the next loss by percents)
+        ts.start_epoch(0)
+        for step in range(3):
             images = torch.randn(N, 3, 448, 448, generator=torch.Generator().manual_seed(10 + step)).cuda()
             _, target = synth.make_loss_inputs(N, S, seed=20 + step, p_obj=0.1)
             l_ours = float(ts.step(images, target.cuda()))
             # the reference step (train.py:157-172) with the stock loss
             it += 1
-            lr = learning_rate_policy(it, 1, lr, LR_ADJUST_MAP)
+            lr = learning_rate_policy(it, 0, lr, LR_ADJUST_MAP)
             for g in opt.param_groups:
                 g["lr"] = lr
             pred = twin(images)
@@ -100,10 +104,14 @@ def test_train_step_equals_the_reference_step_with_the_stock_loss():
             pred.backward(g_ref.cuda())
             opt.step()
             assert abs(l_ours - l_ref) <= 1e-5 * abs(l_ref), (graph, step, l_ours, l_ref)
-        assert ts.lr == lr == 0.001
+        assert ts.lr == lr == pytest.approx(3e-6)
+        # the parameter UPDATES agree (the deltas are ~1e-5, so fp32 storage of the parameters itself limits the
+        # comparison to a few 1e-4 relative; cuDNN's backward adds its own last-bit noise)
         worst = 0.0
-        for (n1, p1), (n2, p2) in zip(ts.net.named_parameters(), twin.named_parameters()):
-            d = float((p1 - p2).abs().max())
-            scale = float(p2.abs().max()) + 1e-12
-            worst = max(worst, d / scale)
-        assert worst <= 2e-5, (graph, worst)
+        for p0, p1, p2 in zip(init, ts.net.parameters(), twin.parameters()):
+            d1, d2 = (p1.detach() - p0), (p2.detach() - p0)
+            scale = float(d2.abs().max())
+            if scale > 0:
+                worst = max(worst, float((d1 - d2).abs().max()) / scale)
+            assert scale > 0 or float(d1.abs().max()) == 0
+        assert worst <= 5e-3, (graph, worst)

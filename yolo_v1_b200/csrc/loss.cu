@@ -257,22 +257,34 @@ int loss_launch_chunk_impl(const void* pred, const int64_t ps[4], int pred_dtype
 
   // Small single-chunk calls (train.py:38-41 trains with 12 x 14 x 14 = 2 352 cells; BASELINE config 1 is 1 568):
   // one cluster, no workspace to reset, no fix-up pass (loss_small.cu).
+  const int D = 5 * B + C;
+  const bool bf = pred_dtype == YOLO1_DTYPE_BF16;
+  const bool aligned16 = (uintptr_t)pred % 16 == 0 && (uintptr_t)target % 16 == 0 && (!grad || (uintptr_t)grad % 16 == 0);
   const bool one_chunk = (chunk_flags & 3) == 3;
-  if (variant == kVariantSmall && !(one_chunk && cells > 0 && cells <= loss_small_max_cells())) return YOLO1_ERR_UNSUPPORTED;
-  if (one_chunk && cells > 0 && cells <= loss_small_max_cells() && (variant == 0 || variant == kVariantSmall))
-    return launch_loss_small(p, pred_dtype == YOLO1_DTYPE_BF16, grad != nullptr, stream);
-  if (variant == kVariantNoSmall) variant = 0;
+  if (one_chunk && cells > 0 && cells <= kSmallTryCells && (variant == 0 || variant == kVariantSmall)) {
+    int layout = 0;
+    if (!lists && B == 2 && C == 20 && aligned16 && contiguous(ts, S, D)) {
+      if (contiguous(ps, S, D) && (!grad || contiguous(gs, S, D))) layout = 1;
+      else if (planar(ps, S, D) && (!grad || planar(gs, S, D))) layout = 2;
+    }
+    const int rc = launch_loss_small(p, bf, grad != nullptr, layout, stream);
+    if (rc != YOLO1_ERR_UNSUPPORTED || variant == kVariantSmall) return rc;   // too large: the streaming kernels
+  } else if (variant == kVariantSmall) {
+    return YOLO1_ERR_UNSUPPORTED;
+  }
+  if (variant == kVariantNoSmall || variant == kVariantSmall) variant = 0;
 
   if (chunk_flags & 1) YOLO1_CUDA_TRY(cudaMemsetAsync(workspace, 0, offsetof(LossWs, partial), stream));
 
-  const int D = 5 * B + C;
   const bool fast = variant >= 0 && B == 2 && C == 20 && contiguous(ps, S, D) && contiguous(ts, S, D) &&
-                    (!grad || contiguous(gs, S, D)) && (uintptr_t)pred % 16 == 0 && (uintptr_t)target % 16 == 0 &&
-                    (!grad || (uintptr_t)grad % 16 == 0);
-  const bool bf = pred_dtype == YOLO1_DTYPE_BF16;
+                    (!grad || contiguous(gs, S, D)) && aligned16;
   if (variant == kVariantHostMapped) {  // pointers are device-visible HOST memory (host_ctx.cu)
     if (!fast || bf || p.logits || p.list_mode) return YOLO1_ERR_UNSUPPORTED;
     return grad ? launch_hostmapped<true>(p, stream) : launch_hostmapped<false>(p, stream);
+  }
+  if (variant >= kVariantSparse && variant < kVariantSparse + 3) {
+    if (!fast || bf || p.logits) return YOLO1_ERR_UNSUPPORTED;
+    return launch_loss_sparse(p, grad != nullptr, variant - kVariantSparse, stream);
   }
   if (fast) {
     return launch_loss_nhwc(p, bf, grad != nullptr, variant, stream);

@@ -79,7 +79,11 @@ int launch_loss_ws(const LossParams& p, bool bf16, bool has_grad, bool is_planar
                    cudaStream_t stream);
 // small calls (loss_small.cu): one cluster, no workspace; any layout / (B, C) / dtype
 int64_t loss_small_max_cells();
-int launch_loss_small(const LossParams& p, bool bf16, bool has_grad, cudaStream_t stream);
+int launch_loss_small(const LossParams& p, bool bf16, bool has_grad, int layout, cudaStream_t stream);
+constexpr int64_t kSmallTryCells = 16384;   // calls up to this size ask the small path first
+// confidence-first form (loss_sparse.cu): sector reads of target[0] / pred[0:2], full rows for object cells only
+int launch_loss_sparse(const LossParams& p, bool has_grad, int shape, cudaStream_t stream);
+constexpr int kVariantSparse = 40;  // 40, 41, 42: 128 / 64 / 256 cells per tile
 constexpr int kVariantSmall = 30;   // yolo1_loss_fwd_bwd_ex: force the small-call kernel (error when too large)
 constexpr int kVariantNoSmall = 31; // ... or keep a small call on the streaming kernels (A/B measurements)
 
@@ -360,9 +364,10 @@ __device__ __forceinline__ ListTargetS list_targetS(const LossParams& p, int64_t
 
 // ---- fast cell: B = 2, C = 20, channel pairs (conflict-free 64-bit shared accesses) -----------------
 // Returns true when the cell holds an object (target channel 0 == 1, v1Loss.py:28).
+// plain = true (small-call kernel): this is one of the call's first two object cells -- plain form right away.
 template <bool HAS_GRAD, typename PA, typename TA, typename GA>
 __device__ __forceinline__ bool cell_b2c20(const PA& P, const TA& T, const GA& G, const LossParams& k,
-                                           CellSums& s) {
+                                           CellSums& s, bool plain = false) {
   const float2 t01 = T.ld2(0);
   const float2 c01 = P.ld2(0);
   if (t01.x != 1.0f) {
@@ -415,7 +420,7 @@ __device__ __forceinline__ bool cell_b2c20(const PA& P, const TA& T, const GA& G
   const bool paper = k.coord_mode == YOLO1_COORD_PAPER;
   float loc = 0.f, gl[4];
 #pragma unroll
-  for (int d = 0; d < 4; ++d) gl[d] = coord_term(pr[d], gr[d], paper && d < 2, loc);
+  for (int d = 0; d < 4; ++d) gl[d] = coord_term(pr[d], gr[d], plain || (paper && d < 2), loc);
   s.loc += loc;
   if (HAS_GRAD) {
     float dI[4];
