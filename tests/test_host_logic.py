@@ -226,3 +226,63 @@ def test_pair_pretest_never_settles_a_pair_that_dies():
         t = np.clip(f(thr) * (1 + rng.randint(-40, 40, n) * 2.0 ** -23), 0, 1).astype(f)
         z = np.zeros(n, f)
         check(thr, np.stack([z, z, s, s], 1), np.stack([z, z, s, (s * t).astype(f)], 1))
+
+
+def _area_skip(thr, nb=256):
+    """set_threshold() of decode_nms.cu, restated: the smallest bucket distance d whose guaranteed area ratio
+    G(d) = min_f lower(f + d - 1) / lower(f) reaches (1 + 1e-5) / thr (area keys = float bits >> 20: 8 per octave)."""
+    need = (1.0 + 1e-5) / float(np.float32(thr))
+    for d in range(1, nb + 1):
+        g = min(np.ldexp(1.0 + ((f + d - 1) % 8) / 8.0, (f + d - 1) // 8) / (1.0 + f / 8.0) for f in range(8))
+        if g >= need:
+            return d
+    return nb + 1
+
+
+def test_area_pruning_never_skips_a_pair_that_dies():
+    """decode_nms.cu, nms_phase (2): pairs whose area buckets are at least area_skip apart are never tested, on the
+    grounds that IoU <= min(area) / max(area).  numpy float32 emulation of the reference's test (utils/utils.py:166-180)
+    over random and adversarial (nested, nearly equal-ratio) boxes: no pair that dies may be skipped -- with clamped
+    bucket indices too -- and at thr = 0.5 about two thirds of the pairs of a uniform image are skipped."""
+    f = np.float32
+    rng = np.random.RandomState(11)
+    key0 = (127 - 24) << 3
+
+    def check(thr, A, B):
+        thr = f(thr)
+        skip = _area_skip(thr)
+        aa = (A[:, 2] - A[:, 0]) * (A[:, 3] - A[:, 1])
+        ab = (B[:, 2] - B[:, 0]) * (B[:, 3] - B[:, 1])
+        tame = (aa >= f(1e-30)) & (ab >= f(1e-30)) & (aa <= f(1e30)) & (ab <= f(1e30))
+        ka = np.clip((aa.view(np.uint32) >> 20).astype(np.int64) - key0, 0, 255)
+        kb = np.clip((ab.view(np.uint32) >> 20).astype(np.int64) - key0, 0, 255)
+        skipped = np.abs(ka - kb) >= skip
+        ww = np.maximum(np.minimum(B[:, 2], A[:, 2]) - np.maximum(B[:, 0], A[:, 0]), f(0))
+        hh = np.maximum(np.minimum(B[:, 3], A[:, 3]) - np.maximum(B[:, 1], A[:, 1]), f(0))
+        inter = ww * hh
+        assert (inter[tame] <= np.minimum(aa, ab)[tame]).all()      # the monotonicity the bound rests on, in fp32
+        with np.errstate(all="ignore"):
+            dies = ~(inter / ((aa + ab) - inter) <= thr)
+        assert not (tame & skipped & dies).any(), thr
+        return float((tame & skipped).sum()) / max(int(tame.sum()), 1)
+
+    n = 200_000
+    for thr in (0.5, 0.45, 0.25, 0.1, 1.0, 0.99999, 2.0 ** -20, 4.0, 0.005):
+        c, wh = rng.rand(n, 2).astype(f), rng.rand(n, 2).astype(f)
+        A = np.concatenate([c - wh / 2, c + wh / 2], 1).astype(f)
+        c2, wh2 = rng.rand(n, 2).astype(f), rng.rand(n, 2).astype(f)
+        B = np.concatenate([c2 - wh2 / 2, c2 + wh2 / 2], 1).astype(f)
+        frac = check(thr, A, B)
+        if thr == 0.5:
+            assert frac > 0.6, frac
+        # nested boxes: IoU == area ratio exactly (the bound is tight), ratios within a few ulp of 1 / thr and of the
+        # bucket boundaries, at tiny / ordinary / huge scales (the last two exercise the clamped buckets)
+        for scale in (1e-6, 1.0, 1e3):
+            s = (np.exp(rng.uniform(-3, 3, n)) * scale).astype(f)
+            r = (min(float(f(thr)), 1.0) * (1 + rng.randint(-64, 64, n) * 2.0 ** -23)).astype(f)
+            z = np.zeros(n, f)
+            big = np.stack([z, z, s, s], 1)
+            small = np.stack([z, z, s, (s * r).astype(f)], 1)
+            check(thr, big, small)
+            check(thr, small, big)
+    assert _area_skip(0.5) == 10 and _area_skip(1.0) == 2      # a little over one octave at 0.5; neighbours only at 1

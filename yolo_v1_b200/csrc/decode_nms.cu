@@ -9,10 +9,13 @@
 //   decode : per (cell, slot) candidate test, class arg-max (the two slots of a cell share the scan), score,
 //            `double(score) > thresh`, order-preserving compaction (ballot + prefix) = emission order; the image's
 //            maximum confidence rides on the same barrier (it only matters when no confidence exceeds 1e-4)
-//   sort   : rank by counting (score descending, emission index ascending) -- deterministic, no ties left
-//   mask   : suppression bit-matrix; one thread per row of the unordered pairs (wrapped-diagonal enumeration, no idle
-//            lanes); an fp32 pre-test settles the surviving pairs, the rare dead pair ORs its bit in (dies iff
-//            !(IoU <= thr), utils/utils.py:180; the image tile is reused for the matrix)
+//   sort   : exact rank (score descending, emission index ascending) by a counting sort into 256 score buckets and a
+//            comparison inside the bucket only: O(n) instead of the n^2 compares of a rank-by-counting
+//   mask   : suppression bit-matrix.  IoU <= min(area) / max(area), so a pair whose areas differ by more than
+//            1 / thr cannot die: a second counting sort (area buckets, 8 per octave) puts every box next to the only
+//            partners that can matter -- a third of all pairs at thr = 0.5 -- and those are dealt out to the threads
+//            in equal shares; an fp32 pre-test settles the survivors, the few others take the exact test
+//            (dies iff !(IoU <= thr), utils/utils.py:180; the image tile is reused for the matrix)
 //   sweep  : the kept set as the fixed point of K(j) = no i < j with K(i) and M[i][j], a few passes of bit
 //            operations.  A suppressed box never suppresses (iterated semantics of the reference).
 //   store  : kept detections in descending score order (float4 boxes), counts.
@@ -29,9 +32,14 @@ namespace {
 // plus the deferred pair loop rolled (x1) 151.7 / 192.8 (x4: 148.8); the on-the-spot pair loop x4 11.73 at S=14
 // (rolled 11.18).  The kernel is sensitive to its code size (ncu: no_instruction stalls), not only to its
 // instruction count.
-constexpr int kRankUnroll = 4, kPairUnroll = 1, kPair2Unroll = 4;
 constexpr int kMaxCand = 1024;
-constexpr int kKeepA = 64, kRankSum = 96, kKeepB = 128;   // slots of Smem::misc (nms_phase): kept-set words, checksum
+constexpr int kKeepA = 64, kKeepB = 128;            // slots of Smem::misc (sweep): the two copies of the kept-set words
+constexpr int kNotes = 96, kKmin = 97, kKmax = 98, kRankSum = 99, kBar = 100;   // ... (nms_phase): unsettled-pair count, score-key
+                                                                      // range, rank checksum
+constexpr int kRankUnroll = 4, kPairUnroll = 1;      // measured in round 1 (tools/tune_decode.py): the small-grid kernel is
+                                                     // sensitive to its code size, not only to its instruction count
+constexpr int kNB = 256;                             // buckets of the two counting sorts (16-bit counters, two per word)
+constexpr int kAreaKey0 = (127 - 24) << 3;           // area bucket 0 starts at 2^-24; 8 buckets per octave, 32 octaves
 
 struct DecodeParams {
   const void* pred;
@@ -50,6 +58,13 @@ struct DecodeParams {
   // fp32 pre-test of the pair loop (pair_margin): thr_lo = thr (1 - 2^-18) rounded down, thr_k = 1 + thr_lo rounded up;
   // thr_lo = 0 (nothing is ever settled by the pre-test) unless 2^-20 <= thr <= 4
   float thr_lo, thr_k;
+  // area pruning (nms_phase): boxes whose area buckets are at least `area_skip` apart have areas more than 1 / thr
+  // apart, so their IoU cannot exceed thr (set_threshold)
+  int area_skip;
+  // bulk image load (decode_nms_image): dense fp32 [N,S,S,D] tensor on a 16-byte aligned base whose images are a
+  // multiple of 8 bytes -- one cp.async.bulk per image instead of a load / store pair per 8 bytes
+  int bulk_ok;
+  int64_t n_images;
   int s_magic;    // cell / S == (cell * s_magic) >> 16 for every cell of the grid (0: use the division)
   // decode outputs / nms inputs
   float* boxes;
@@ -68,43 +83,64 @@ struct DecodeParams {
 
 // dynamic shared memory layout shared by the three kernels
 struct Smem {
-  float* img;       // [S*S*D]   (decode)   -- aliased by mask after decode
+  float* img;       // [S*S*D]   (decode)   -- the region is reused after decode by the five arrays below
   uint32_t* mask;   // [n * W]
+  int32_t* bidx;    // [max_n]  candidate indices in score-bucket order
+  uint32_t* notes;  // [2 * max_n]  pairs the fp32 pre-test left unsettled: (area position a) << 16 | (area position b)
+  uint32_t* tkey;   // [max_n]  per candidate: (score bucket << 16 | slot in it), later its rank
+  uint32_t* akey;   // [max_n]  per candidate: (area bucket << 16 | slot in it), later its area position
   float4* box;      // [max_n]  candidates in emission order
   float* score;     // [max_n]
   int32_t* cls;     // [max_n]
-  float4* sbox;     // [max_n + max_n/2]  sorted by score, sbox[n + r] = sbox[r] for r < n/2 (wrap-free reads)
-  float* sta;       // [max_n + max_n/2]  thr_lo * area of the sorted boxes, wrapped like sbox
+  float4* abox;     // [max_n]  boxes in area-bucket order         } together exactly the bytes of sbox: the general
+  float* ata;       // [max_n]  thr_lo * area, same order           } pair code (wild images) rebuilds sbox over them
+  int32_t* arank;   // [max_n]  score rank of the box at an area position
+  float4* sbox;     // [max_n + max_n/2]  sorted by score, sbox[n + r] = sbox[r] for r < n/2 (general pair code only)
+  int32_t* lpre;    // [max_n + 1]  partners per area position, then their exclusive prefix (lpre[n] = total)
   int32_t* sidx;    // [max_n]  sorted position -> emission index
   int32_t* keep;    // [max_n]  kept sorted positions
+  uint32_t* hist;   // [kNB]  kNB / 2 words of score-bucket counters, then kNB / 2 of area-bucket counters
   int32_t* misc;    // [160]  0..63 decode scratch / kept count; 64..95 and 128..159 kept-set words of the sweep
-                    //        (128..159 decode scratch before); 96 rank checksum
+                    //        (128..159 decode scratch before); 96..98 note count and score-key range
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 __host__ __device__ inline size_t smem_layout(unsigned char* base, int img_floats, int max_n, Smem* s) {
   const int W = (max_n + 31) / 32;
-  size_t region = (size_t)img_floats * 4;
-  const size_t mask_bytes = (size_t)max_n * W * 4;
-  if (mask_bytes > region) region = mask_bytes;
-  size_t off = 0;
-  if (s) s->img = reinterpret_cast<float*>(base), s->mask = reinterpret_cast<uint32_t*>(base);
-  off += align16(region);
-  if (s) s->sbox = reinterpret_cast<float4*>(base + off);
-  off += (size_t)(max_n + max_n / 2) * 16;
+  const size_t mask_bytes = align16((size_t)max_n * W * 4), n4 = align16((size_t)max_n * 4);
+  size_t region = (size_t)img_floats * 4 + (img_floats ? 16 : 0);   // + the bulk load's alignment slack
+  const size_t after = mask_bytes + n4 /*bidx*/ + 2 * n4 /*notes*/ + n4 /*tkey*/ + n4 /*akey*/;
+  if (after > region) region = after;
+  if (s) {
+    s->img = reinterpret_cast<float*>(base), s->mask = reinterpret_cast<uint32_t*>(base);
+    s->bidx = reinterpret_cast<int32_t*>(base + mask_bytes);
+    s->notes = reinterpret_cast<uint32_t*>(base + mask_bytes + n4);
+    s->tkey = reinterpret_cast<uint32_t*>(base + mask_bytes + 3 * n4);
+    s->akey = reinterpret_cast<uint32_t*>(base + mask_bytes + 4 * n4);
+  }
+  size_t off = align16(region);
+  if (s) {
+    s->sbox = reinterpret_cast<float4*>(base + off);
+    s->abox = reinterpret_cast<float4*>(base + off);
+    s->ata = reinterpret_cast<float*>(base + off + (size_t)max_n * 16);
+    s->arank = reinterpret_cast<int32_t*>(base + off + (size_t)max_n * 20);
+  }
+  off += align16((size_t)(max_n + max_n / 2 + 1) * 16);   // >= 24 max_n: abox + ata + arank
   if (s) s->box = reinterpret_cast<float4*>(base + off);
   off += (size_t)max_n * 16;
   if (s) s->score = reinterpret_cast<float*>(base + off);
-  off += align16((size_t)max_n * 4);
+  off += n4;
   if (s) s->cls = reinterpret_cast<int32_t*>(base + off);
-  off += align16((size_t)max_n * 4);
-  if (s) s->sta = reinterpret_cast<float*>(base + off);
-  off += align16((size_t)(max_n + max_n / 2) * 4);
+  off += n4;
+  if (s) s->lpre = reinterpret_cast<int32_t*>(base + off);
+  off += align16((size_t)(max_n + 1) * 4);
   if (s) s->sidx = reinterpret_cast<int32_t*>(base + off);
-  off += align16((size_t)max_n * 4);
+  off += n4;
   if (s) s->keep = reinterpret_cast<int32_t*>(base + off);
-  off += align16((size_t)max_n * 4);
+  off += n4;
+  if (s) s->hist = reinterpret_cast<uint32_t*>(base + off);
+  off += kNB * 4;
   if (s) s->misc = reinterpret_cast<int32_t*>(base + off);
   off += 160 * 4;
   return off;
@@ -335,17 +371,11 @@ __device__ __forceinline__ bool iou_exceeds(float inter, float u, const DecodePa
   return !(inter / u <= p.iou_thr);
 }
 
-// The suppression matrix.  Every unordered pair is visited exactly once: thread <-> row i, which it keeps in
-// registers, against the columns (i + d) mod n for the offsets d = 1 .. n/2 (for even n the last offset meets each
-// pair from both ends, so it runs over i < n/2 only).  Lanes are consecutive rows, so for a given d they read
-// consecutive boxes (conflict-free 128-bit loads).  When the CTA has room for several threads per row
-// (blockDim >= 2 n) the offsets are split between them.  The few pairs that die set their bit with a
-// shared-memory atomic OR; the earlier box of the pair (lower sorted position) plays the reference's box i.
-// The bit lands in the later box's column (column j, bit i: kept i kills j), which is what the sweep reads.
+// ---- the pairs ---------------------------------------------------------------------------------------------
+// intersection and union term of box A (area_a) with box Bx, by the reference's op sequence (:166-179).
 // FINITE = true: every coordinate of the image is an ordinary number (|c| < 1e18) and every area lies in
 // [1e-30, 1e30], so clamp(min=)/clamp(max=) are plain max/min (one FMNMX each), the intersection is symmetric in
 // the two boxes, nothing overflows or underflows, and the fp32 pre-test (pair_margin) applies.
-// intersection and union term of box A (area_a) with box Bx, by the reference's op sequence (:166-179)
 template <bool FINITE>
 __device__ __forceinline__ void pair_terms(const float4& A, float area_a, const float4& Bx, bool a_first, float& inter,
                                            float& u) {
@@ -368,103 +398,61 @@ __device__ __forceinline__ void pair_terms(const float4& A, float area_a, const 
   u = (area_a + area_b) - inter;   // ovr = inter / (a_i + a_j - inter)
 }
 
-// the exact test of one pair; sets the matrix bit when the later box dies
-__device__ __forceinline__ void pair_settle(const Smem& sm, int n, int W, int i, int jj, float inter, float u,
-                                            const DecodeParams& p) {
-  if (!iou_exceeds(inter, u, p)) return;
-  const int j = jj < n ? jj : jj - n;
-  const int lo = min(i, j), hi = max(i, j);
+// the later box of a dying pair gets the earlier one's bit: column hi (sorted position), bit lo -- "kept lo kills hi",
+// which is what the sweep reads
+__device__ __forceinline__ void set_kill(const Smem& sm, int W, int ra, int rb, const DecodeParams& p) {
+  const int lo = min(ra, rb), hi = max(ra, rb);
   if (p.per_class && sm.cls[sm.sidx[lo]] != sm.cls[sm.sidx[hi]]) return;
-  atomicOr(&sm.mask[hi * W + (lo >> 5)], 1u << (lo & 31));   // column hi: the earlier boxes that kill it
+  atomicOr(&sm.mask[hi * W + (lo >> 5)], 1u << (lo & 31));
 }
 
-// The pair loop's pre-test (tame images only: every |coordinate| < 1e18 and every area in [1e-30, 1e30]).
+// The pre-test of a pair (tame images only: every |coordinate| < 1e18 and every area in [1e-30, 1e30]).
 // With ta = fl32(thr_lo * area) per box and k = thr_k, the sign of
 //     m = fma(inter, k, -(ta_a + ta_b))            (one fp32 add, one fused multiply-add: exact sign)
 // settles the common case: m < 0  =>  inter (1 + thr_lo) < thr_lo (a_a + a_b) (1 + 3 * 2^-24)
 //                                  =>  inter < thr_lo (1 + 7 * 2^-24) u      (u = fl(fl(a_a + a_b) - inter), inter <= u)
 //                                  =>  inter / u < thr  =>  fl32(inter / u) <= thr: the pair survives (:180).
 // (thr_lo carries a margin of 2^-18 = 64 * 2^-24; an inverted box has inter = 0 and u > 0 and survives as well.)
-// That is 12 instructions per pair instead of 20 for inter, the union and a compare; whatever the sign does not
-// settle (m >= 0: the pair dies or is within 4e-6 of the threshold) takes the exact test.
+// 12 instructions instead of 20 for inter, the union and a compare; whatever the sign does not settle (m >= 0: the
+// pair dies or is within 4e-6 of the threshold) is noted and takes the exact test afterwards.
 __device__ __forceinline__ float pair_margin(const float4& A, float nta_a, const float4& Bx, float ta_b, float k) {
   const float ww = fmaxf(fminf(Bx.z, A.z) - fmaxf(Bx.x, A.x), 0.f);
   const float hh = fmaxf(fminf(Bx.w, A.w) - fmaxf(Bx.y, A.y), 0.f);
   return fmaf(ww * hh, k, nta_a - ta_b);
 }
 
-// DEFER = true: the pair loop notes unsettled columns and works them off per 32-column round (grids of up to 128
-// candidates: +2..8 %); false: exact test on the spot (14x14 grids: deferring measured -17 % on densely overlapping
-// boxes, where the notes per lane are many and uneven, and the extra registers cost a resident CTA).
-template <bool FINITE, bool DEFER>
-__device__ __forceinline__ void nms_row(const Smem& sm, int n, int W, int i, int d0, int d1, const DecodeParams& p) {
+// General pair code (images with a NaN / infinite / huge coordinate or an area that is not an ordinary positive
+// number, thresholds outside the pre-test's range, or more unsettled pairs than the note list holds): every
+// unordered pair takes the exact test, the reference's op sequence with its clamp semantics.  Thread <-> row i of the
+// score-sorted boxes against the columns (i + d) mod n for d = 1 .. n/2 (for even n the last offset meets each pair
+// from both ends, so it runs over i < n/2 only); the sorted boxes are repeated behind their end, so the column walk
+// needs no modulo.  When the CTA has room for several threads per row the offsets are split between them.
+__device__ __forceinline__ void general_row(const Smem& sm, int n, int W, int i, int d0, int d1, const DecodeParams& p) {
   const float4 A = sm.sbox[i];
-  const int jend = i + d1;   // columns may run past n: the head of the sorted boxes is repeated behind their end
-  auto settle = [&](int c) {   // the exact test of column c (rare on tame images)
-    float in0, u0;
-    pair_terms<FINITE>(A, (A.z - A.x) * (A.w - A.y), sm.sbox[c], c < n, in0, u0);   // :159 area of box i
-    pair_settle(sm, n, W, i, c, in0, u0, p);
-  };
-  if constexpr (!FINITE) {   // general code: every pair takes the exact test
-    for (int jj = i + d0; jj <= jend; ++jj) settle(jj);
-  } else if constexpr (!DEFER) {
-    const float nta = -sm.sta[i], k = p.thr_k;
-    int jj = i + d0;
-#pragma unroll kPair2Unroll
-    for (; jj < jend; jj += 2) {   // two columns per trip
-      const float m0 = pair_margin(A, nta, sm.sbox[jj], sm.sta[jj], k);
-      const float m1 = pair_margin(A, nta, sm.sbox[jj + 1], sm.sta[jj + 1], k);
-      if (fmaxf(m0, m1) < 0.f) continue;
-      if (!(m0 < 0.f)) settle(jj);
-      if (!(m1 < 0.f)) settle(jj + 1);
-    }
-    if (jj == jend && !(pair_margin(A, nta, sm.sbox[jj], sm.sta[jj], k) < 0.f)) settle(jj);
-  } else {
-    // The streaming loop only notes which columns the pre-test settled (the sign bit of m, shifted into a word:
-    // one funnel shift per column, 32 columns per round); the others are few, and taking the exact test right
-    // there would drag the whole warp through ~30 instructions for one or two lanes each time.  After the round
-    // the lanes work their unsettled columns off together.
-    const float nta = -sm.sta[i], k = p.thr_k;
-    for (int base = i + d0; base <= jend; base += 32) {
-      const int cend = min(base + 31, jend);
-      unsigned sure = 0;   // bit (cend - c) set: column c survives
-      int jj = base;
-#pragma unroll kPairUnroll
-      for (; jj < cend; jj += 2) {   // two columns per trip
-        const float m0 = pair_margin(A, nta, sm.sbox[jj], sm.sta[jj], k);
-        const float m1 = pair_margin(A, nta, sm.sbox[jj + 1], sm.sta[jj + 1], k);
-        sure = __funnelshift_l(__float_as_uint(m0), sure, 1);
-        sure = __funnelshift_l(__float_as_uint(m1), sure, 1);
-      }
-      if (jj == cend) sure = __funnelshift_l(__float_as_uint(pair_margin(A, nta, sm.sbox[jj], sm.sta[jj], k)), sure, 1);
-      unsigned todo = ~sure & (0xffffffffu >> (31 - (cend - base)));
-      while (todo) {
-        const int b = __ffs(todo) - 1;
-        todo &= todo - 1;
-        settle(cend - b);
-      }
-    }
+  const float area_a = (A.z - A.x) * (A.w - A.y);   // :159 area of box i
+  for (int jj = i + d0; jj <= i + d1; ++jj) {
+    float inter, u;
+    pair_terms<false>(A, area_a, sm.sbox[jj], jj < n, inter, u);
+    if (iou_exceeds(inter, u, p)) set_kill(sm, W, i, jj < n ? jj : jj - n, p);
   }
 }
-
-template <bool FINITE, bool DEFER>
-__device__ __forceinline__ void nms_pairs(const Smem& sm, int n, int W, const DecodeParams& p) {
+__device__ __forceinline__ void general_pairs(const Smem& sm, int n, int W, const DecodeParams& p) {
   const int H = n >> 1;
-  if (2 * n > (int)blockDim.x) {   // one thread per row (the usual case: no division)
+  if (2 * n > (int)blockDim.x) {
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       const int d1 = (!(n & 1) && i >= H) ? H - 1 : H;
-      if (d1 >= 1) nms_row<FINITE, DEFER>(sm, n, W, i, 1, d1, p);
+      if (d1 >= 1) general_row(sm, n, W, i, 1, d1, p);
     }
     return;
   }
-  const int G = (int)blockDim.x / n, K = (H + G - 1) / G;   // few candidates: G threads share a row's offsets
+  const int G = (int)blockDim.x / n, K = (H + G - 1) / G;
   for (int t = threadIdx.x; t < n * G; t += blockDim.x) {
     const int g = t / n, i = t - g * n;
     const int d0 = g * K + 1;
     int d1 = min(d0 + K - 1, H);
     if (!(n & 1) && d1 == H && i >= H) --d1;
     if (d0 > d1) continue;
-    nms_row<FINITE, DEFER>(sm, n, W, i, d0, d1, p);
+    general_row(sm, n, W, i, d0, d1, p);
   }
 }
 
@@ -558,29 +546,246 @@ __device__ __forceinline__ int sweep_phase(const Smem& sm, int n, int W) {
   return sm.misc[0];
 }
 
-// before the barrier that precedes nms_phase: clear what the phase accumulates into with atomics
-__device__ __forceinline__ void nms_prepare(const Smem& sm, int max_n) {
-  if (threadIdx.x == 0) sm.misc[kRankSum] = 0;
-  for (int t = threadIdx.x; t < max_n; t += blockDim.x) sm.sidx[t] = 0;   // ranks that collide before the tie pass leave holes: keep them in range
+// ---- counting sorts -----------------------------------------------------------------------------------------
+// kNB buckets with 16-bit counters, two per word (n <= 1024).  add() returns the element's slot inside its bucket.
+__device__ __forceinline__ int hist_add(uint32_t* h, int b) {
+  const int sh = (b & 1) << 4;
+  return (int)((atomicAdd(&h[b >> 1], 1u << sh) >> sh) & 0xffffu);
+}
+__device__ __forceinline__ int hist_get(const uint32_t* h, int b) { return (int)((h[b >> 1] >> ((b & 1) << 4)) & 0xffffu); }
+// counts -> exclusive starts, in place; one warp, 8 buckets (4 words) per lane.  start(kNB) is n (hist_start).
+__device__ __forceinline__ void hist_scan(uint32_t* h, int lane) {
+  uint32_t w[4];
+  int c[8], total = 0;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    w[t] = h[lane * 4 + t];
+    c[2 * t] = (int)(w[t] & 0xffffu), c[2 * t + 1] = (int)(w[t] >> 16);
+    total += c[2 * t] + c[2 * t + 1];
+  }
+  int incl = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  int run = incl - total;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int s0 = run, s1 = run + c[2 * t];
+    run = s1 + c[2 * t + 1];
+    h[lane * 4 + t] = (uint32_t)s0 | ((uint32_t)s1 << 16);
+  }
+}
+__device__ __forceinline__ int hist_start(const uint32_t* h, int b, int n) { return b >= kNB ? n : hist_get(h, b); }
+
+// scores as unsigned keys in their float order (torch.sort(descending=True), :161): NaN above everything, -0 == +0
+__device__ __forceinline__ uint32_t score_key(float s) {
+  if (s != s) return 0xffffffffu;
+  if (s == 0.f) return 0x80000000u;
+  const uint32_t b = __float_as_uint(s);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-template <bool DEFER>
-__device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodeParams& p) {
-  const int lane = threadIdx.x & 31;
+// before the barrier that precedes nms_phase: clear what the phase accumulates into with atomics
+// (SMALL: only the area buckets are used -- 128 words, one 16-byte store in each of 32 threads)
+template <bool SMALL>
+__device__ __forceinline__ void nms_prepare(const Smem& sm) {
+  uint4* h4 = reinterpret_cast<uint4*>(SMALL ? sm.hist + kNB / 2 : sm.hist);
+  for (int t = threadIdx.x; t < (SMALL ? kNB / 8 : kNB / 4); t += blockDim.x) h4[t] = make_uint4(0u, 0u, 0u, 0u);
+  if (threadIdx.x == 0) sm.misc[kNotes] = 0, sm.misc[kKmin] = -1, sm.misc[kKmax] = 0, sm.misc[kRankSum] = 0;
+}
+// the suppression matrix starts empty (16-byte stores; the region behind it is 16-byte padded)
+__device__ __forceinline__ void clear_mask(const Smem& sm, int words) {
+  uint4* m4 = reinterpret_cast<uint4*>(sm.mask);
+  for (int t = threadIdx.x; t < ((words + 3) >> 2); t += blockDim.x) m4[t] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// ---- phase: sort + suppression matrix + sweep (utils/utils.py:150-184).  Returns the kept count. -------------
+//  (1) score order.  Candidates are dealt into kNB buckets by the leading bits of their score key (the image's own
+//      key range mapped onto the buckets); a prefix over the buckets places each bucket, and inside a bucket -- one
+//      or two candidates -- the rank is settled by comparing scores, ties by emission index (canonical, SURVEY B.3;
+//      equal scores always share a bucket).  O(n) where rank-by-counting compared all n^2 pairs.
+//  (2) area order.  IoU = inter / (a + b - inter) <= min(a, b) / max(a, b) (inter <= min(a, b) holds in fp32 too:
+//      min / max / subtract / multiply are monotone), so a pair with max > min / thr survives whatever its position:
+//      fl32(inter / u) <= (min / max)(1 + 5 * 2^-24).  Buckets of the area's float bits >> 20 (8 per octave, exact
+//      powers of two between octaves) put every box next to the partners that can matter: positions up to the end
+//      of bucket b + area_skip - 1 (set_threshold derives area_skip with a 1e-5 margin).  At thr = 0.5 that is a
+//      third of all pairs.  Clamping the bucket index only ever shrinks a distance, so it never skips a live pair.
+//  (3) the partner lists of all boxes are laid end to end (prefix sum) and cut into equal shares, one per thread:
+//      every lane runs the same number of pre-tests whatever its boxes' list lengths.  A pair the pre-test does not
+//      settle is noted (shared-memory list) and takes the exact test after the loop, all threads together.
+__device__ __forceinline__ int nms_phase_large(const Smem& sm, int n, const DecodeParams& p) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int W = (n + 31) >> 5;
-  // the suppression matrix starts empty; dead pairs are OR-ed in below
-  for (int t = threadIdx.x; t < n * W; t += blockDim.x) sm.mask[t] = 0u;
-  // :161 order = scores descending; ties -> lower emission index first (canonical).
-  // Rank by counting the larger scores, four per shared-memory load.  Without equal scores the ranks are a
-  // permutation and add up to n (n - 1) / 2; a smaller sum means ties (rare): those images are ranked again with
-  // the tie rule.
-  bool wild = false;   // a NaN, infinite or huge coordinate, an area that is not an ordinary positive number: the
-                       // image takes the general pair code
-  int ranks = 0;
-  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+  uint32_t* hs = sm.hist;            // score buckets
+  uint32_t* ha = sm.hist + kNB / 2;  // area buckets
+  clear_mask(sm, n * W);   // dead pairs are OR-ed in by the exact tests
+  // ---- the image's score-key range ----
+  uint32_t kmin = 0xffffffffu, kmax = 0u;
+  for (int k = tid; k < n; k += nt) {
+    const uint32_t key = score_key(sm.score[k]);
+    kmin = min(kmin, key), kmax = max(kmax, key);
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin), kmax = __reduce_max_sync(0xffffffffu, kmax);
+  if (lane == 0) {
+    atomicMin(reinterpret_cast<unsigned*>(&sm.misc[kKmin]), kmin);
+    atomicMax(reinterpret_cast<unsigned*>(&sm.misc[kKmax]), kmax);
+  }
+  __syncthreads();
+  kmax = (uint32_t)sm.misc[kKmax];
+  const uint32_t range = kmax - (uint32_t)sm.misc[kKmin];
+  const int shift = range ? max(0, 32 - __clz(range) - 8) : 0;   // (kmax - key) >> shift < kNB
+  // ---- slots in the score buckets and in the area buckets; is the image tame? ----
+  bool wild = p.thr_lo == 0.f;   // a threshold outside the pre-test's range: general code for every pair
+  for (int k = tid; k < n; k += nt) {
+    const int db = (int)((kmax - score_key(sm.score[k])) >> shift);   // bucket 0 holds the largest scores
+    sm.tkey[k] = ((uint32_t)db << 16) | (uint32_t)hist_add(hs, db);
+    const float4 b = sm.box[k];
+    const float area = (b.z - b.x) * (b.w - b.y);  // :159
+    wild |= !(fabsf(b.x) < 1.0e18f && fabsf(b.y) < 1.0e18f && fabsf(b.z) < 1.0e18f && fabsf(b.w) < 1.0e18f &&
+              area >= 1.0e-30f && area <= 1.0e30f);
+    const int ab = min(max((int)(__float_as_uint(area) >> 20) - kAreaKey0, 0), kNB - 1);
+    sm.akey[k] = ((uint32_t)ab << 16) | (uint32_t)hist_add(ha, ab);
+  }
+  const bool tame = !__syncthreads_or(wild);
+  if (warp == 0) hist_scan(hs, lane);
+  if (warp == (nwarps > 1 ? 1 : 0)) hist_scan(ha, lane);
+  __syncthreads();
+  // ---- into bucket order ----
+  for (int k = tid; k < n; k += nt) {
+    const uint32_t t = sm.tkey[k];
+    sm.bidx[hist_get(hs, (int)(t >> 16)) + (int)(t & 0xffffu)] = k;
+    if (tame) {
+      const uint32_t a = sm.akey[k];
+      const int ab = (int)(a >> 16), apos = hist_get(ha, ab) + (int)(a & 0xffffu);
+      const float4 b = sm.box[k];
+      sm.abox[apos] = b, sm.ata[apos] = p.thr_lo * ((b.z - b.x) * (b.w - b.y));
+      sm.akey[k] = (uint32_t)apos;
+      // partners: the later positions up to the end of bucket ab + area_skip - 1
+      sm.lpre[apos] = max(hist_start(ha, ab + p.area_skip, n) - 1 - apos, 0);
+    }
+  }
+  __syncthreads();
+  // ---- exact rank inside the score bucket; the partner counts become offsets (last warp, meanwhile) ----
+  if (tame && warp == nwarps - 1) {
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int v = base + lane < n ? sm.lpre[base + lane] : 0;
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+      }
+      if (base + lane < n) sm.lpre[base + lane] = carry + incl - v;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) sm.lpre[n] = carry;
+  }
+  for (int k = tid; k < n; k += nt) {
+    const int db = (int)(sm.tkey[k] >> 16), q0 = hist_get(hs, db), q1 = hist_start(hs, db + 1, n);
     const float s = sm.score[k];
-    // four independent fp32 counters (one set-on-compare and one add per score; counts < 2^24 are exact)
-    float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;
+    const bool s_nan = s != s;
+    int rank = q0;
+    for (int q = q0; q < q1; ++q) {
+      const int m = sm.bidx[q];
+      const float v = sm.score[m];
+      const bool v_nan = v != v;   // NaN scores (stand-alone yolo1_nms only) order before every number
+      rank += (v > s) || (v_nan && !s_nan) || ((v == s || (v_nan && s_nan)) && m < k);
+    }
+    sm.sidx[rank] = k;
+    sm.tkey[k] = (uint32_t)rank;
+    if (tame) sm.arank[sm.akey[k]] = rank;
+  }
+  __syncthreads();
+  bool general = !tame;
+  if (tame) {
+    // ---- pre-tests: equal shares of the concatenated partner lists ----
+    const int T = sm.lpre[n], share = (T + nt - 1) / nt, cap = 2 * p.max_n;
+    int idx = tid * share;
+    const int end = min(idx + share, T);
+    if (idx < end) {
+      int lo = 0, hi = n - 1;   // the row that holds pair idx: the last position whose offset is <= idx
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (sm.lpre[mid] <= idx) lo = mid; else hi = mid - 1;
+      }
+      int row = lo, row_end = sm.lpre[row + 1], col = row + 1 + (idx - sm.lpre[row]);
+      float4 A = sm.abox[row];
+      float nta = -sm.ata[row];
+      const float k = p.thr_k;
+      for (; idx < end; ++idx, ++col) {
+        if (idx >= row_end) {   // next row with partners
+          do {
+            ++row;
+            row_end = sm.lpre[row + 1];
+          } while (idx >= row_end);
+          col = row + 1 + (idx - sm.lpre[row]);
+          A = sm.abox[row], nta = -sm.ata[row];
+        }
+        if (!(pair_margin(A, nta, sm.abox[col], sm.ata[col], k) < 0.f)) {
+          const int slot = atomicAdd(&sm.misc[kNotes], 1);
+          if (slot < cap) sm.notes[slot] = ((uint32_t)row << 16) | (uint32_t)col;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- exact tests of the noted pairs ----
+    const int notes = sm.misc[kNotes];
+    general = notes > cap;   // more than the list holds (e.g. a stack of identical boxes): general code instead
+    if (!general) {
+      for (int t = tid; t < notes; t += nt) {
+        const uint32_t nn = sm.notes[t];
+        const int a = (int)(nn >> 16), b = (int)(nn & 0xffffu);
+        const float4 A = sm.abox[a];
+        float inter, u;
+        pair_terms<true>(A, (A.z - A.x) * (A.w - A.y), sm.abox[b], true, inter, u);
+        if (iou_exceeds(inter, u, p)) set_kill(sm, W, sm.arank[a], sm.arank[b], p);
+      }
+    }
+    __syncthreads();
+  }
+  if (general) {   // uniform
+    for (int k = tid; k < n; k += nt) {
+      const int r = (int)sm.tkey[k];
+      const float4 b = sm.box[k];
+      sm.sbox[r] = b;
+      if (r < (n >> 1)) sm.sbox[n + r] = b;   // wrap copy: row i reads the columns i+1 .. i+n/2 without a modulo
+    }
+    __syncthreads();
+    general_pairs(sm, n, W, p);
+    __syncthreads();
+  }
+  return sweep_phase<false>(sm, n, W);
+}
+
+// Grids of up to 128 candidates (96-thread CTAs, 16 to an SM).  Measured (B200, S = 7): the bucketed score order and
+// the equal-share pair loop above cut the instruction count but not the time -- their phases are chains of dependent
+// shared-memory operations (atomics that return slots, a binary search, bucket walks) behind eight CTA barriers, and a
+// 3-warp CTA cannot hide them (90 M images / s at 4096 images against 110 M before).  So here:
+//   * the score rank stays a rank by counting (four scores per 128-bit load, independent fp32 counters: pure
+//     issue throughput, no dependent chain; a checksum detects equal scores, which are ranked again with the tie rule),
+//   * the area buckets ride along: a candidate's bucket slot is requested before its rank loop and read after it,
+//   * thread <-> box in area order, against its partners i+1 .. i+L (the later positions up to the end of bucket
+//     b + area_skip - 1); the loop only collects the sign bits of the pre-test (32 columns per round) and the lanes
+//     work their unsettled columns off together after the round.  A warp runs as long as its longest partner list.
+__device__ __forceinline__ int nms_phase_small(const Smem& sm, int n, const DecodeParams& p) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int W = (n + 31) >> 5;
+  uint32_t* ha = sm.hist + kNB / 2;
+  clear_mask(sm, n * W);
+  bool wild = p.thr_lo == 0.f;
+  int ranks = 0;
+  for (int k = tid; k < n; k += nt) {
+    const float s = sm.score[k];
+    const float4 b = sm.box[k];
+    const float area = (b.z - b.x) * (b.w - b.y);  // :159
+    wild |= !(fabsf(b.x) < 1.0e18f && fabsf(b.y) < 1.0e18f && fabsf(b.z) < 1.0e18f && fabsf(b.w) < 1.0e18f &&
+              area >= 1.0e-30f && area <= 1.0e30f);
+    const int ab = min(max((int)(__float_as_uint(area) >> 20) - kAreaKey0, 0), kNB - 1);
+    const int aslot = hist_add(ha, ab);
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f;   // counts < 2^24 are exact
     const int n4 = n & ~3;
 #pragma unroll kRankUnroll
     for (int m = 0; m < n4; m += 4) {
@@ -590,62 +795,136 @@ __device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodePara
     for (int m = n4; m < n; ++m) r0 += sm.score[m] > s ? 1.f : 0.f;
     const int rank = (int)((r0 + r1) + (r2 + r3));
     ranks += rank;
-    const float4 b = sm.box[k];
-    const float area = (b.z - b.x) * (b.w - b.y);  // :159
-    wild |= !(fabsf(b.x) < 1.0e18f && fabsf(b.y) < 1.0e18f && fabsf(b.z) < 1.0e18f && fabsf(b.w) < 1.0e18f &&
-              area >= 1.0e-30f && area <= 1.0e30f);
-    const float ta = p.thr_lo * area;   // pair_margin
-    sm.sbox[rank] = b, sm.sta[rank] = ta, sm.sidx[rank] = k;
-    // wrap copy: row i reads the columns i+1 .. i+n/2 without a modulo
-    if (rank < (n >> 1)) sm.sbox[n + rank] = b, sm.sta[n + rank] = ta;
+    sm.sidx[rank] = k;
+    sm.tkey[k] = (uint32_t)rank;
+    sm.akey[k] = ((uint32_t)ab << 16) | (uint32_t)aslot;
   }
   ranks = __reduce_add_sync(0xffffffffu, ranks);
   if (lane == 0 && ranks) atomicAdd(&sm.misc[kRankSum], ranks);
-  const int any_wild = __syncthreads_or(wild);
-  if (sm.misc[kRankSum] != n * (n - 1) / 2) {   // uniform: equal scores somewhere
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+  const bool tame = !__syncthreads_or(wild);
+  if (sm.misc[kRankSum] != n * (n - 1) / 2) {   // uniform: equal (or NaN) scores somewhere -- again, with the tie rule
+    for (int k = tid; k < n; k += nt) {
       const float s = sm.score[k];
-      // NaN scores (stand-alone yolo1_nms only: a decoded NaN score never passes `> thresh`) order before every
-      // number, as torch.sort(descending=True) places them (:161); among themselves by index like any tie
-      const bool s_nan = s != s;
+      const bool s_nan = s != s;   // NaN scores (stand-alone yolo1_nms only) order before every number (:161)
       int rank = 0;
       for (int m = 0; m < n; ++m) {
         const float v = sm.score[m];
         const bool v_nan = v != v;
         rank += (v > s) || (v_nan && !s_nan) || ((v == s || (v_nan && s_nan)) && m < k);
       }
+      sm.sidx[rank] = k;
+      sm.tkey[k] = (uint32_t)rank;
+    }
+  }
+  if (tame) {
+    if (warp == 0) hist_scan(ha, lane);
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+      const uint32_t a = sm.akey[k];
+      const int ab = (int)(a >> 16), apos = hist_get(ha, ab) + (int)(a & 0xffffu);
       const float4 b = sm.box[k];
-      const float ta = p.thr_lo * ((b.z - b.x) * (b.w - b.y));
-      sm.sbox[rank] = b, sm.sta[rank] = ta, sm.sidx[rank] = k;
-      if (rank < (n >> 1)) sm.sbox[n + rank] = b, sm.sta[n + rank] = ta;
+      sm.abox[apos] = b, sm.ata[apos] = p.thr_lo * ((b.z - b.x) * (b.w - b.y));
+      sm.arank[apos] = (int)sm.tkey[k];
+      sm.lpre[apos] = max(hist_start(ha, ab + p.area_skip, n) - 1 - apos, 0);
     }
     __syncthreads();
+    const float k = p.thr_k;
+    for (int i = tid; i < n; i += nt) {
+      const int jend = i + sm.lpre[i];
+      if (jend == i) continue;
+      const float4 A = sm.abox[i];
+      const float nta = -sm.ata[i];
+      for (int base = i + 1; base <= jend; base += 32) {
+        const int cend = min(base + 31, jend);
+        unsigned sure = 0;   // bit (cend - c) set: column c survives
+        int jj = base;
+#pragma unroll kPairUnroll
+        for (; jj < cend; jj += 2) {   // two columns per trip
+          const float m0 = pair_margin(A, nta, sm.abox[jj], sm.ata[jj], k);
+          const float m1 = pair_margin(A, nta, sm.abox[jj + 1], sm.ata[jj + 1], k);
+          sure = __funnelshift_l(__float_as_uint(m0), sure, 1);
+          sure = __funnelshift_l(__float_as_uint(m1), sure, 1);
+        }
+        if (jj == cend) sure = __funnelshift_l(__float_as_uint(pair_margin(A, nta, sm.abox[jj], sm.ata[jj], k)), sure, 1);
+        unsigned todo = ~sure & (0xffffffffu >> (31 - (cend - base)));
+        while (todo) {   // the exact test of a column the pre-test left open (rare)
+          const int c = cend - (__ffs(todo) - 1);
+          todo &= todo - 1;
+          float inter, u;
+          pair_terms<true>(A, (A.z - A.x) * (A.w - A.y), sm.abox[c], true, inter, u);
+          if (iou_exceeds(inter, u, p)) set_kill(sm, W, sm.arank[i], sm.arank[c], p);
+        }
+      }
+    }
+    __syncthreads();
+  } else {
+    __syncthreads();   // the ranks of the tie pass
+    for (int k = tid; k < n; k += nt) {
+      const int r = (int)sm.tkey[k];
+      const float4 b = sm.box[k];
+      sm.sbox[r] = b;
+      if (r < (n >> 1)) sm.sbox[n + r] = b;
+    }
+    __syncthreads();
+    general_pairs(sm, n, W, p);
+    __syncthreads();
   }
-  // suppression matrix: column j, bit i (i < j) set iff box j dies when box i is kept (:166-180)
-  if (any_wild)
-    nms_pairs<false, false>(sm, n, W, p);
+  return sweep_phase<true>(sm, n, W);
+}
+
+template <bool SMALL>
+__device__ __forceinline__ int nms_phase(const Smem& sm, int n, const DecodeParams& p) {
+  if constexpr (SMALL)
+    return nms_phase_small(sm, n, p);
   else
-    nms_pairs<true, DEFER>(sm, n, W, p);
-  __syncthreads();
-  return sweep_phase<DEFER>(sm, n, W);
+    return nms_phase_large(sm, n, p);
 }
 
 // ---- kernels ---------------------------------------------------------------------------------------------
-template <typename E, bool DEFER>
+template <typename E, bool SMALL>
 __device__ __forceinline__ void decode_nms_image(const DecodeParams& p) {
   extern __shared__ __align__(16) unsigned char raw[];
   Smem sm;
   smem_layout(raw, p.S * p.S * (5 * p.B + p.C), p.max_n, &sm);
   const int64_t n = blockIdx.x;
-  load_image<E>(p, n, sm.img);
-  nms_prepare(sm, p.max_n);
-  __syncthreads();
-  const int cand = decode_phase<DEFER>(p, sm);
-  const int kept = cand > 0 ? nms_phase<DEFER>(sm, cand, p) : 0;
+  // Image load.  Dense fp32 tensors: ONE bulk (TMA) copy issued by thread 0 (UBLKCP; completion on an mbarrier)
+  // replaces eight 8-byte load / store pairs per thread -- 8 % of the kernel's instructions, and the bytes land
+  // without passing through registers.  Bulk copies move multiples of 16 bytes between 16-byte aligned addresses,
+  // while an image of S*S*D floats may start 8 bytes off (odd images of a 7x7x30 tensor): the copy then starts 8
+  // bytes early (inside the previous image) and `img` points 8 bytes into the buffer; an image whose rounded-up copy
+  // would end beyond the tensor (the last one) takes the per-thread loads.
+  bool bulk = false;
+  if (sizeof(E) == 4 && p.bulk_ok) {
+    const uint32_t img_bytes = (uint32_t)(p.S * p.S * (5 * p.B + p.C)) * 4u;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.pred) + n * (int64_t)img_bytes;
+    const uint32_t mis = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+    const uint32_t bytes = (img_bytes + mis + 15u) & ~15u;
+    bulk = !(n == p.n_images - 1 && bytes > img_bytes + mis);
+    if (bulk) {
+      uint64_t* bar = reinterpret_cast<uint64_t*>(sm.misc + kBar);
+      if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(bar, bytes);
+        bulk_g2s(raw, src - mis, bytes, bar, policy_evict_first());
+      }
+      sm.img = reinterpret_cast<float*>(raw + mis);
+      nms_prepare<SMALL>(sm);
+      __syncthreads();          // the barrier is initialised before anyone polls it
+      mbar_wait(bar, 0);
+    }
+  }
+  if (!bulk) {
+    load_image<E>(p, n, sm.img);
+    nms_prepare<SMALL>(sm);
+    __syncthreads();
+  }
+  const int cand = decode_phase<SMALL>(p, sm);
+  const int kept = cand > 0 ? nms_phase<SMALL>(sm, cand, p) : 0;
   for (int t = threadIdx.x; t < kept; t += blockDim.x) {
     const int src = sm.keep[t], e = sm.sidx[src];
     const int64_t dst = n * p.max_n + t;
-    reinterpret_cast<float4*>(p.out_boxes)[dst] = sm.sbox[src];
+    reinterpret_cast<float4*>(p.out_boxes)[dst] = sm.box[e];
     p.out_scores[dst] = sm.score[e];
     p.out_cls[dst] = sm.cls[e];
     if (p.keep) p.keep[dst] = e;
@@ -663,9 +942,9 @@ __device__ __forceinline__ void decode_nms_image(const DecodeParams& p) {
   }
 }
 
-template <typename E, bool DEFER>
+template <typename E, bool SMALL>
 __global__ void decode_nms_kernel(const __grid_constant__ DecodeParams p) {
-  decode_nms_image<E, DEFER>(p);
+  decode_nms_image<E, SMALL>(p);
 }
 // grids of up to 128 candidates run 96-thread CTAs, 16 to an SM: 40 registers (the pair loop would take 48 unbounded)
 template <>
@@ -702,7 +981,7 @@ __global__ void decode_kernel(const __grid_constant__ DecodeParams p) {
   if (threadIdx.x == 0) p.counts[n] = cand;
 }
 
-template <bool DEFER>
+template <bool SMALL>
 __device__ __forceinline__ void nms_image(const DecodeParams& p) {
   extern __shared__ __align__(16) unsigned char raw[];
   Smem sm;
@@ -717,17 +996,17 @@ __device__ __forceinline__ void nms_image(const DecodeParams& p) {
     sm.score[t] = p.scores[src];
     sm.cls[t] = p.cls ? p.cls[src] : 0;
   }
-  nms_prepare(sm, p.max_n);
+  nms_prepare<SMALL>(sm);
   __syncthreads();
-  const int kept = cnt > 0 ? nms_phase<DEFER>(sm, cnt, p) : 0;
+  const int kept = cnt > 0 ? nms_phase<SMALL>(sm, cnt, p) : 0;
   for (int t = threadIdx.x; t < p.max_n; t += blockDim.x)
     p.keep[n * p.max_n + t] = t < kept ? sm.sidx[sm.keep[t]] : 0;
   if (threadIdx.x == 0) p.out_counts[n] = kept;
 }
 
-template <bool DEFER>
+template <bool SMALL>
 __global__ void nms_kernel(const __grid_constant__ DecodeParams p) {
-  nms_image<DEFER>(p);
+  nms_image<SMALL>(p);
 }
 template <>
 __global__ void __launch_bounds__(96, 16) nms_kernel<true>(const __grid_constant__ DecodeParams p) {
@@ -777,7 +1056,7 @@ int check_decode_args(const void* pred, const int64_t st[4], int dtype, int64_t 
 void set_threshold(DecodeParams& p, float thr) {
   p.iou_thr = thr;
   p.thr_fast = (thr >= 0.f && thr < 1.0e30f) ? 1 : 0;
-  p.thr_mid = 0.0, p.thr_tie_ok = 0, p.thr_lo = 0.f, p.thr_k = 1.f;
+  p.thr_mid = 0.0, p.thr_tie_ok = 0, p.thr_lo = 0.f, p.thr_k = 1.f, p.area_skip = kNB + 1;
   if (p.thr_fast) {
     const float up = nextafterf(thr, INFINITY);
     p.thr_mid = 0.5 * ((double)thr + (double)up);
@@ -789,6 +1068,24 @@ void set_threshold(DecodeParams& p, float thr) {
     if (thr >= 0x1p-20f && thr <= 4.f) {   // pair_margin: range in which its products stay ordinary numbers
       p.thr_lo = nextafterf((float)((double)thr * (1.0 - 0x1p-18)), 0.f);
       p.thr_k = nextafterf((float)(1.0 + (double)p.thr_lo), INFINITY);
+      // Area pruning (nms_phase): area keys are float bits >> 20, i.e. 8 steps per octave with boundaries at
+      // 2^e (1 + f / 8).  Two boxes whose keys differ by at least d have areas a < lower(k + 1) and
+      // b >= lower(k + d): b / a > G(d) = min over f of lower(f + d - 1) / lower(f).  The pair cannot die once
+      // G(d) >= (1 + 1e-5) / thr (IoU <= a / b, five fp32 roundings); area_skip is the smallest such d.
+      const double need = (1.0 + 1e-5) / (double)thr;
+      p.area_skip = kNB + 1;
+      for (int d = 1; d <= kNB; ++d) {
+        double g = 1e300;
+        for (int f = 0; f < 8; ++f) {
+          const int t = f + d - 1;
+          const double r = ldexp(1.0 + (t % 8) / 8.0, t / 8) / (1.0 + f / 8.0);
+          if (r < g) g = r;
+        }
+        if (g >= need) {
+          p.area_skip = d;
+          break;
+        }
+      }
     }
   }
 }
@@ -881,8 +1178,13 @@ int yolo1_decode_nms(const void* pred, const int64_t pred_strides[4], int pred_d
   set_threshold(p, iou_thr);
   p.out_boxes = out_boxes, p.out_scores = out_scores, p.out_cls = out_cls, p.out_counts = out_counts;
   p.keep = keep_idx, p.cand_counts = cand_counts;
+  const int Dch = 5 * B + C;
+  p.n_images = N;
+  p.bulk_ok = pred_dtype == YOLO1_DTYPE_F32 && pred_strides[3] == 1 && pred_strides[2] == Dch &&
+              pred_strides[1] == (int64_t)S * Dch && pred_strides[0] == (int64_t)S * S * Dch &&
+              (uintptr_t)pred % 16 == 0 && ((int64_t)S * S * Dch * 4) % 8 == 0;
   const int img = S * S * (5 * B + C);
-  const bool defer = p.max_n <= 128;   // see nms_row
+  const bool defer = p.max_n <= 128;   // up to 128 candidates: 96-thread CTAs and the one-warp register sweep
   if (pred_dtype == YOLO1_DTYPE_BF16)
     return defer ? launch<decode_nms_kernel<__nv_bfloat16, true>>(p, N, img, (cudaStream_t)stream)
                  : launch<decode_nms_kernel<__nv_bfloat16, false>>(p, N, img, (cudaStream_t)stream);

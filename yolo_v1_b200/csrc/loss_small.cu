@@ -39,14 +39,15 @@ namespace {
 namespace cg = cooperative_groups;
 
 constexpr int kSmallCtas = 8;        // portable cluster size
-constexpr int kSmallThreads = 256;
+constexpr int kSmallThreads = 256;   // generic form
+constexpr int kResThreads = 512;     // resident form: 2 352 cells (train.py:38-41) are 294 per CTA -- one pass
 constexpr int kSmallMaxPerThread = 1;   // generic form: one cell per thread (2 048 cells); see the header comment
 
 struct SmallShared {
   double part[kSmallCtas][4];      // rank 0 only: the CTAs' partial sums, pushed through DSMEM
   uint32_t pair[kSmallCtas][2];    // every CTA: the (inverted) first-two-object indices of each peer
-  double red[kSmallThreads / 32][4];
-  uint32_t redm[kSmallThreads / 32][2];
+  double red[kResThreads / 32][4];
+  uint32_t redm[kResThreads / 32][2];
 };
 
 // cell index -> element offset with 32-bit divisions (q < 16 384 here; cell_offset divides 64-bit numbers)
@@ -170,7 +171,7 @@ struct ResidentPlan {
 };
 
 template <typename E, bool HAS_GRAD, bool PLANAR, bool SIG>
-__global__ void __launch_bounds__(kSmallThreads) loss_small_resident_kernel(const __grid_constant__ LossParams p,
+__global__ void __launch_bounds__(kResThreads) loss_small_resident_kernel(const __grid_constant__ LossParams p,
                                                                             const ResidentPlan plan) {
   constexpr int D = 30;
   __shared__ SmallShared sh;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kSmallThreads) loss_small_resident_kernel(cons
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned rank = cluster.block_rank();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int nwarps = kSmallThreads / 32;
+  constexpr int nwarps = kResThreads / 32;
   const int SS = p.S * p.S;
   const int64_t total_units = p.cells / plan.unit;
   const int64_t u0 = (int64_t)rank * plan.units_per_cta;
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(kSmallThreads) loss_small_resident_kernel(cons
 
   // ---- which of my cells hold an object; the call's first two (v1Loss.py:101) across the cluster ---------------
   uint32_t m1 = 0, m2 = 0;
-  for (int c = tid; c < my_cells; c += kSmallThreads)
+  for (int c = tid; c < my_cells; c += kResThreads)
     if (st[c * D] == 1.0f) note_object(m1, m2, c0 + c);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(kSmallThreads) loss_small_resident_kernel(cons
   CellSums sums = {0.f, 0.f, 0.f, 0.f};
   using PIn = typename SmemIn<E>::type;
   using GOut = typename SmemOut<E>::type;
-  for (int c = tid; c < my_cells; c += kSmallThreads) {
+  for (int c = tid; c < my_cells; c += kResThreads) {
     const uint32_t inv = 0xFFFFFFFFu - (uint32_t)(c0 + c);
     const bool plain = ref_mode && (inv == f1 || inv == f2);
     const SmemInF32 T{st + c * D};
@@ -333,10 +334,10 @@ int launch_resident_t(const LossParams& p, const ResidentPlan& plan, cudaStream_
   const size_t smem = (((size_t)plan.units_per_cta * plan.pred_unit_bytes + 127) & ~(size_t)127) +
                       (size_t)plan.units_per_cta * plan.tgt_unit_bytes;
   static KernelPrep prep;
-  if (int rc = prepare_kernel(prep, kern, kSmallThreads, smem, false, nullptr, nullptr)) return rc;
+  if (int rc = prepare_kernel(prep, kern, kResThreads, smem, false, nullptr, nullptr)) return rc;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(kSmallCtas, 1, 1);
-  cfg.blockDim = dim3(kSmallThreads, 1, 1);
+  cfg.blockDim = dim3(kResThreads, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
