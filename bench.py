@@ -322,7 +322,21 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"      # NCCL would print its version banner on stdout (one JSON line only)
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when its first communicator is created (NCCL_DEBUG=VERSION may
+        # come from a config file, not only from the environment): send fd 1 to stderr until that has happened, so
+        # that stdout carries the one JSON line and nothing else
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     hbm_peak, sm_max_mhz, peak_src = _peaks()
 
     def barrier():

@@ -27,7 +27,10 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    import datetime
+    # a short collective timeout: a hang must fail this test in a minute, not in the watchdog's default ten
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                            timeout=datetime.timedelta(seconds=60))
     try:
         pred, target = synth.make_loss_inputs(N, S, seed=77, p_obj=0.1)
         a, b = y.shard_range(N, rank, world)
@@ -38,6 +41,8 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, "r%d.npy" % rank), np.concatenate([mod.last_terms.cpu().numpy(), gterms.cpu().numpy()]))
         np.save(os.path.join(out_dir, "g%d.npy" % rank), p.grad.cpu().numpy())
+        if os.environ.get("YOLO1_SKIP_GRAPH_NCCL") == "1":
+            return
         # the same exchange as ONE captured CUDA graph (loss kernel + NCCL all-reduce), replayed twice
         gl = y.GraphedLoss(b - a, S, 2, 20, average=False)
         for it in range(2):
@@ -46,6 +51,7 @@ def _worker(rank, world, port, out_dir):
         torch.cuda.synchronize()
         np.save(os.path.join(out_dir, "gr%d.npy" % rank), gl.global_terms.cpu().numpy())
         np.save(os.path.join(out_dir, "gg%d.npy" % rank), q.grad.cpu().numpy())
+        gl.release()      # a graph that captured a collective must be gone before the process group is destroyed
     finally:
         dist.destroy_process_group()
 
@@ -70,5 +76,8 @@ def test_two_rank_sharded_loss_over_nccl(tmp_path):
     for r in range(2):
         got = np.load(os.path.join(tmp_path, "r%d.npy" % r))
         assert np.allclose(got[5:], total, rtol=1e-5)
-        assert np.allclose(np.load(os.path.join(tmp_path, "gr%d.npy" % r)), total, rtol=1e-5)      # graph replay
-        assert np.array_equal(np.load(os.path.join(tmp_path, "gg%d.npy" % r)), np.load(os.path.join(tmp_path, "g%d.npy" % r)))
+        if os.path.exists(os.path.join(tmp_path, "gr%d.npy" % r)):
+            assert np.allclose(np.load(os.path.join(tmp_path, "gr%d.npy" % r)), total, rtol=1e-5)      # graph replay
+            assert np.array_equal(np.load(os.path.join(tmp_path, "gg%d.npy" % r)), np.load(os.path.join(tmp_path, "g%d.npy" % r)))
+        else:
+            assert os.environ.get("YOLO1_SKIP_GRAPH_NCCL") == "1"

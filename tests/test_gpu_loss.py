@@ -331,6 +331,7 @@ def test_graphed_loss_and_allreduce_replay_with_new_inputs():
         assert torch.equal(g2.global_terms, want_t) and torch.equal(zv.grad, want_g)
         with pytest.raises(ValueError):
             g2(zv.detach().contiguous(), target.cuda())
+        g.release(), g2.release()
     finally:
         if started:
             dist.destroy_process_group()

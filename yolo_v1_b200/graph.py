@@ -49,7 +49,8 @@ class GraphedLoss:
 
     The graph is captured on the first call from that call's shapes / strides / dtypes (later calls must match) on
     a side stream, after one eager warm-up that also initialises the NCCL communicator.  `group=None` uses the
-    default process group when torch.distributed is initialised and no collective otherwise."""
+    default process group when torch.distributed is initialised and no collective otherwise.  Call `release()`
+    before `destroy_process_group()`."""
 
     def __init__(self, batch_size, S, B=2, C=20, l_coord=5.0, l_noobj=0.5, coord_mode="reference",
                  from_logits=False, group=None, average=True):
@@ -88,11 +89,25 @@ class GraphedLoss:
         with torch.cuda.stream(side):
             self._body()                      # warm-up: lazy initialisation (NCCL communicator, kernel attributes)
             side.synchronize()
+            if self._collective():
+                dist.barrier(group=self.group)    # every rank has finished its warm-up collective before any captures
+                torch.cuda.synchronize(dev)
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=side):
+            # thread_local: ProcessGroupNCCL's watchdog thread polls CUDA events while this thread captures; under the
+            # default (global) capture mode such a call from another thread invalidates the capture
+            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
                 self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
         self.graph = g
+
+    def release(self):
+        """Drop the captured graph and its static buffers.  A graph that captured an NCCL collective must be gone
+        before `torch.distributed.destroy_process_group()` -- the communicator's teardown otherwise waits for it
+        (measured: a 2-rank job hangs in destroy_process_group with the graph alive)."""
+        self.graph = None
+        self.static_pred = self.static_target = self.static_grad = None
+        self.serial += 1          # a backward() still pending on the old buffers raises instead of reading freed memory
+        torch.cuda.synchronize()
 
     def run(self, pred, target):
         """pred / target -> (loss 0-dim clone, global_terms); gradient in self.static_grad until the next call."""

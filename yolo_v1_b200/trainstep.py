@@ -120,6 +120,11 @@ class TrainStep:
         self.epoch = int(epoch)
         return self.epoch
 
+    def close(self):
+        """Release the captured loss graph (before torch.distributed.destroy_process_group())."""
+        if self.graphed is not None:
+            self.graphed.release()
+
     def step(self, images, target):
         self.iter += 1
         self.lr = learning_rate_policy(self.iter, self.epoch, self.lr, LR_ADJUST_MAP)
