@@ -114,7 +114,7 @@ def test_planar_fast_path_all_shapes(S, N, dtype):
         pred = pred.to(torch.bfloat16)
     o_terms, o_grad = O.loss(pred.float().numpy(), target.numpy(), batch_size=N)
     planar = pred.cuda().permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
-    for variant in (0, 1, 20):
+    for variant in (0, 1, 20, 31, 50, 51):   # 31: streaming default; 50: confidence-first planar kernel; 51: dense planar
         _, grad, terms = y.yolo_loss_fused(planar, target.cuda(), batch_size=N, variant=variant)
         assert grad.stride() == planar.stride()
         if dtype == "f32":
@@ -125,6 +125,54 @@ def test_planar_fast_path_all_shapes(S, N, dtype):
             assert np.all(np.abs(g - o_grad) <= np.abs(o_grad) * 2.0 ** -8 + 1e-30)
         _, _, t2 = y.yolo_loss_fused(planar, target.cuda(), batch_size=N, variant=variant, want_grad=False)
         assert torch.equal(t2, terms)
+
+
+@pytest.mark.parametrize("S,N", [(14, 4000), (7, 9000)])
+def test_planar_confidence_first_kernel_many_tiles_per_cta(S, N):
+    """csrc/loss_planar_sparse.cu keeps its gradient tiles in shared memory between tiles and only clears what an
+    object cell wrote two tiles earlier: run it with several tiles per CTA and an object in every fourth cell, in every
+    form (dense target, object lists, fused sigmoid head, bf16, forward only), against the oracle and against the dense
+    planar kernels (variant 51)."""
+    y = _y()
+    pred, target = synth.make_loss_inputs(N, S, seed=77 + S, p_obj=0.25)
+    o_terms, o_grad = O.loss(pred.numpy(), target.numpy(), batch_size=N)
+    tc = target.cuda()
+    planar = pred.cuda().permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+    _, grad, terms = y.yolo_loss_fused(planar, tc, batch_size=N, variant=50)
+    assert grad.stride() == planar.stride()
+    _check(terms, grad, o_terms, o_grad, ("planar sparse", S, N))
+    _, g51, t51 = y.yolo_loss_fused(planar, tc, batch_size=N, variant=51)
+    assert torch.equal(g51, grad) and torch.allclose(t51, terms, rtol=1e-6)
+    _, _, t0 = y.yolo_loss_fused(planar, tc, batch_size=N, variant=50, want_grad=False)
+    assert torch.allclose(t0, terms, rtol=1e-6)
+    # object lists (4-byte ownership map instead of the target rows)
+    objmask = target[..., 0] == 1
+    idx = objmask.nonzero()
+    bx = target[idx[:, 0], idx[:, 1], idx[:, 2], 2:6]
+    cxcy = (bx[:, :2] + torch.stack([idx[:, 2], idx[:, 1]], 1).float()) / S
+    boxes = torch.cat([cxcy, bx[:, 2:]], 1).contiguous()
+    labels = target[idx[:, 0], idx[:, 1], idx[:, 2], 10:].argmax(1).to(torch.int32)
+    offs = torch.zeros(N + 1, dtype=torch.int64)
+    offs[1:] = objmask.reshape(N, -1).sum(1).cumsum(0)
+    enc = y.encode_targets(boxes.cuda(), labels.cuda(), offs.cuda(), S)
+    oe_terms, oe_grad = O.loss(pred.numpy(), enc.cpu().numpy(), batch_size=N)
+    _, gl, tl = y.yolo_loss_from_objects(planar, boxes.cuda(), labels.cuda(), offs.cuda(), batch_size=N, variant=50)
+    _check(tl, gl, oe_terms, oe_grad, ("planar sparse lists", S, N))
+    # fused sigmoid head, fp32 and bf16 logits
+    z = torch.logit(pred.clamp(1e-4, 1 - 1e-4))
+    zp = z.cuda().permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
+    # (the logits entry point has no variant argument: fp32 whole-image tiles of a 14x14 grid take the
+    #  confidence-first kernel by default, 7x7 grids the dense planar kernel -- both against the oracle)
+    p64 = torch.sigmoid(z.double())
+    os_terms, os_grad = O.loss(p64.float().numpy(), target.numpy(), batch_size=N)
+    want = os_grad.astype(np.float64) * (p64 * (1 - p64)).numpy()
+    _, gs, ts_ = y.yolo_loss_fused(zp, tc, batch_size=N, from_logits=True)
+    assert np.all(np.abs(ts_.cpu().numpy() - os_terms) <= TOL * np.abs(os_terms) + 1e-7)
+    assert np.abs(gs.cpu().numpy() - want).max() <= TOL * np.abs(want).max()
+    pb = planar.to(torch.bfloat16)
+    _, gb, tb = y.yolo_loss_fused(pb, tc, batch_size=N, variant=50)
+    _, gb2, tb2 = y.yolo_loss_fused(pb, tc, batch_size=N, variant=51)
+    assert torch.equal(gb, gb2) and torch.allclose(tb, tb2, rtol=1e-6)
 
 
 def test_batch_size_divisor_lambdas_and_paper_mode():

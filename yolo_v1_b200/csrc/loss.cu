@@ -303,6 +303,16 @@ int loss_launch_chunk_impl(const void* pred, const int64_t ps[4], int pred_dtype
   if (fast_planar) {
     if (variant == 20)  // force the warp-specialised kernel whatever the tile size
       return launch_loss_ws(p, bf, grad != nullptr, true, tile_imgs * S * S, 3, stream);
+    // confidence-first form (loss_planar_sparse.cu): reads planes 0-1 of pred and gathers the rest for object cells
+    // only -- 248 instead of 360 B / cell.  Its tiles wait for the lane that gathers, so it is latency- rather than
+    // byte-bound; measured (profiles/tune_planar_r2.log, config-3 size) it wins where the dense kernels are weakest:
+    // fp32, whole 14x14 images per tile, dense target (0.686 vs 0.736 ms; fused head 0.731 vs 0.809), and loses for
+    // bf16, object lists and 7x7 grids.  50 forces it, 51 forces the dense planar kernels (A/B runs).
+    const int sparse_imgs = planar_tile_imgs(S, esz, 224, lists != nullptr);
+    if (variant == kVariantPlanarSparse || (variant != 51 && !bf && !lists && sparse_imgs * S * S >= 160)) {
+      const int rc = launch_loss_planar_sparse(p, bf, grad != nullptr, sparse_imgs, stream);
+      if (rc != YOLO1_ERR_UNSUPPORTED || variant == kVariantPlanarSparse) return rc;
+    }
     return launch_loss_planar(p, bf, grad != nullptr, tile_imgs, stream);
   }
   if (bf) return grad ? launch_generic<__nv_bfloat16, true>(p, stream) : launch_generic<__nv_bfloat16, false>(p, stream);

@@ -84,6 +84,9 @@ constexpr int64_t kSmallTryCells = 16384;   // calls up to this size ask the sma
 // confidence-first form (loss_sparse.cu): sector reads of target[0] / pred[0:2], full rows for object cells only
 int launch_loss_sparse(const LossParams& p, bool has_grad, int shape, cudaStream_t stream);
 constexpr int kVariantSparse = 40;  // 40, 41, 42: 128 / 64 / 256 cells per tile
+// the same idea where it pays: the channel-planar view, whose confidence planes are contiguous (loss_planar_sparse.cu)
+int launch_loss_planar_sparse(const LossParams& p, bool bf16, bool has_grad, int tile_imgs, cudaStream_t stream);
+constexpr int kVariantPlanarSparse = 50;   // force it; 51 = force the dense planar kernels
 constexpr int kVariantSmall = 30;   // yolo1_loss_fwd_bwd_ex: force the small-call kernel (error when too large)
 constexpr int kVariantNoSmall = 31; // ... or keep a small call on the streaming kernels (A/B measurements)
 
@@ -276,7 +279,7 @@ struct SigOut {
   Out out;
   __device__ __forceinline__ void st2(int c, float x, float y) const { out.st2(c, x, y); }   // zeros only
   __device__ __forceinline__ void st2p(int c, float x, float y, float px, float py) const {
-    out.st2(c, x * (px * (1.0f - px)), y * (py * (1.0f - py)));
+    out.st2p(c, x * (px * (1.0f - px)), y * (py * (1.0f - py)), px, py);   // (st2p: a writer may drop plain st2 zeros)
   }
 };
 
