@@ -547,7 +547,7 @@ def main():
         nbytes = pred.numel() * 4
         n_obj = int((target[..., 0] == 1).sum().item())
         # the transfer mode is a property of the host and of how many GPUs share it: measured, all ranks together
-        best_mode, mode_ms = yhost.autotune_zero_copy(ctx, hp, ht, hg, N_LOSS, modes=(2, 0), repeats=2,
+        best_mode, mode_ms = yhost.autotune_zero_copy(ctx, hp, ht, hg, N_LOSS, modes=(2, 1, 4, 0), repeats=2,
                                                       barrier=barrier, reduce_max=max_over_ranks)
 
         def run_e2e(mode):
@@ -571,14 +571,15 @@ def main():
         v_best, ms_best = run_e2e(best_mode)
         # bytes over PCIe per step: staged = both tensors up, gradient down; in place = one 32-byte sector of target
         # and of pred per cell (object cells in full), gradient down
-        h2d = {0: 2 * nbytes, 2: cells * 64 + n_obj * 240}[best_mode]
+        sect = cells * 32 + n_obj * 120           # one tensor read sector-wise: 32 B per cell, object cells in full
+        h2d = {0: 2 * nbytes, 1: nbytes + sect, 2: 2 * sect, 3: nbytes + sect, 4: 2 * sect}[best_mode]
         e2e = {"value": v_best, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": nbytes + 20,
                "steps": e2e_steps, "ms_per_step": ms_best, "mode": best_mode, "mode_name": yhost.ZERO_COPY_MODES[best_mode],
                "mode_selection_ms": {str(k): v for k, v in mode_ms.items()},
                "numa_bound_alloc": bool(numa.cpus),
                "api": "yolo1_loss_fwd_bwd_host: pinned host pred+target in, host grad+terms out; transfer mode "
-                      "(0 = staged copy-engine pipeline, 2 = one kernel reading the needed sectors in place) picked "
-                      "by yolo_v1_b200.host.autotune_zero_copy on all ranks together"}
+                      "(0 = staged copy-engine pipeline, 2 = one kernel reading the needed sectors in place, 1 / 4 = "
+                      "mixed) picked by yolo_v1_b200.host.autotune_zero_copy on all ranks together"}
         ctx.close()
         del hg
 

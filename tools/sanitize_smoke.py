@@ -13,9 +13,13 @@ for S, N in ((7, 37), (14, 9)):
     pred, target = synth.make_loss_inputs(N, S, seed=1, p_obj=0.2, device="cuda")
     planar = pred.permute(0, 3, 1, 2).contiguous().permute(0, 2, 3, 1)
     for p in (pred, planar, pred.to(torch.bfloat16), planar.to(torch.bfloat16)):
-        for variant in (0, 8, -1):
-            y.yolo_loss_fused(p, target, batch_size=N, variant=variant)
-            y.yolo_loss_fused(p, target, batch_size=N, variant=variant, want_grad=False)
+        for variant in (0, 8, -1, 31, 50):      # 0: small-call cluster kernel here; 31: streaming; 50: confidence-first planar
+            try:
+                y.yolo_loss_fused(p, target, batch_size=N, variant=variant)
+                y.yolo_loss_fused(p, target, batch_size=N, variant=variant, want_grad=False)
+            except RuntimeError:
+                assert variant == 50      # only defined for the planar view
+
         y.yolo_loss_fused(p, target, batch_size=N, from_logits=True)
     mod = y.YOLOLossV1(N, S, 2, 20)
     q = pred.clone().requires_grad_(True)
@@ -39,6 +43,9 @@ for S, N in ((7, 37), (14, 9)):
     labels = torch.randint(0, 20, (50,))
     offs = torch.tensor([0, 3, 3, 10, 25, 50])
     y.encode_targets(boxes.cuda(), labels.cuda(), offs.cuda(), S)
+    bb, ll, oo = y.pack_objects([torch.rand(3, 4) * 0.8 + 0.1 for _ in range(N)], [torch.randint(0, 20, (3,)) for _ in range(N)])
+    y.yolo_loss_from_objects(pred, bb.cuda(), ll.cuda(), oo.cuda(), batch_size=N)
+    y.yolo_loss_from_objects(planar, bb.cuda(), ll.cuda(), oo.cuda(), batch_size=N, variant=31)
 g = torch.Generator().manual_seed(0)
 xy = torch.rand(1000, 2, generator=g) * 0.8
 y.nms(torch.cat([xy, xy + 0.1], 1), torch.rand(1000, generator=g), 0.5)
