@@ -515,8 +515,12 @@ def main():
     gplanar = torch.empty_like(planar)
     ms = time_device(lambda: y.yolo_loss_fused(planar, target, batch_size=N_LOSS, out_grad=gplanar, out_terms=terms,
                                                workspace=ws), mod_steps)
-    variants["planar_nchw_view"] = {"ms_per_step": ms, "hbm_gbs": BYTES_PER_CELL * cells / (ms * 1e-3) / 1e9,
-                                    "frac": BYTES_PER_CELL * cells / (ms * 1e-3) / 1e9 / hbm_peak}
+    # (fp32 whole-image tiles of a 14x14 grid take the confidence-first kernel: it moves 248 B / cell, not 360)
+    variants["planar_nchw_view"] = {"ms_per_step": ms, "kernel": "loss_planar_sparse_kernel (reads pred planes 0-1, "
+                                    "gathers object cells)", "bytes_per_cell": 248,
+                                    "hbm_gbs": 248 * cells / (ms * 1e-3) / 1e9,
+                                    "frac": 248 * cells / (ms * 1e-3) / 1e9 / hbm_peak,
+                                    "dense_equivalent_gbs": BYTES_PER_CELL * cells / (ms * 1e-3) / 1e9}
     del planar, gplanar
 
     # ---------------- stress variant of SURVEY.md 8(d): every second cell holds an object ----------------------

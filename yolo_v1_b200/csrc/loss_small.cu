@@ -284,7 +284,6 @@ __global__ void __launch_bounds__(kResThreads) loss_small_resident_kernel(const 
     for (int w = 0; w < nwarps; ++w) a += sh.red[w][tid];
     *cluster.map_shared_rank(&sh.part[rank][tid], 0) = a;
   }
-  if (HAS_GRAD && tid == 32 && my_units > 0) bulk_wait_all<0>();   // the store has landed before this CTA may exit
   cluster.sync();
   if (rank == 0 && tid == 0) {
     double acc[4] = {0, 0, 0, 0};
@@ -299,6 +298,8 @@ __global__ void __launch_bounds__(kResThreads) loss_small_resident_kernel(const 
     p.terms[3] = (float)(acc[3] * ib);
     p.terms[4] = (float)(((double)p.lc * acc[0] + acc[1] + (double)p.ln * acc[2] + acc[3]) * ib);
   }
+  // the gradient store drains behind the reduction; the issuing thread keeps its CTA (and the tile) alive until then
+  if (HAS_GRAD && tid == 32 && my_units > 0) bulk_wait_all<0>();
 }
 
 constexpr size_t kResidentSmem = 216 * 1024;   // dynamic shared memory a CTA may use for its two ranges
