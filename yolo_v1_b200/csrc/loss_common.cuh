@@ -599,58 +599,65 @@ __device__ __noinline__ void block_epilogue(CellSums s, uint32_t m1, uint32_t m2
   __syncthreads();
   if (!s_last) return;
   // ---- last CTA of the launch ----
+  // Three jobs run side by side: warp 0 adds up the per-CTA partial sums; lane 0 of two other warps re-evaluates one
+  // of the call's first two object cells each.  (One lane doing both after the reduction was a chain of dependent
+  // global loads, ~7.5 us per launch whatever the call size: tools/loss_size_sweep.py, reference vs paper mode.)
+  __shared__ double fixloc[2];
   __threadfence();
+  const unsigned long long pr = *reinterpret_cast<volatile unsigned long long*>(&ws->pair);
+  const uint32_t c[2] = {(uint32_t)(pr >> 32), (uint32_t)pr};   // c[1] != 0 implies c[0] != 0
+  const unsigned int carry = *reinterpret_cast<volatile unsigned int*>(&ws->carry);
+  if (threadIdx.x < 2) fixloc[threadIdx.x] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    // v1Loss.py:101 `[:2]`: object t of this chunk is one of the first two of the CALL -> plain form
+    if (warp == (t + 1) % nwarps && lane == 0 && c[t] != 0u && carry + t < 2 && p.coord_mode == YOLO1_COORD_REFERENCE) {
+      const int64_t q = (int64_t)(0xFFFFFFFFu - c[t]);
+      const E* zq = reinterpret_cast<const E*>(p.pred) + cell_offset(p.ps, q, p.S);
+      GlobIn<E> P{zq, p.ps[3], p.logits != 0};
+      GlobOut<E> G{HAS_GRAD ? reinterpret_cast<E*>(p.grad) + cell_offset(p.gs, q, p.S) : nullptr, p.gs[3], zq,
+                   p.ps[3], p.logits != 0};
+      CellSums d = {0.f, 0.f, 0.f, 0.f};
+      if (p.list_mode) {
+        cell_generic<HAS_GRAD, true>(P, list_targetS(p, q), G, p, d);
+      } else {
+        GlobIn<float> T{p.target + cell_offset(p.ts, q, p.S), p.ts[3], false};
+        cell_generic<HAS_GRAD, true>(P, T, G, p, d);
+      }
+      fixloc[t] = (double)d.loc;
+    }
+  }
+  double t4[4] = {0, 0, 0, 0};
   if (warp == 0) {
-    double t4[4] = {0, 0, 0, 0};
     for (unsigned int b = lane; b < gridDim.x; b += 32) {
 #pragma unroll
       for (int t = 0; t < 4; ++t) t4[t] += __ldcg(&ws->partial[b][t]);
     }
 #pragma unroll
     for (int t = 0; t < 4; ++t) t4[t] = warp_sum(t4[t]);
-    if (lane == 0) {
-      const unsigned long long pr = *reinterpret_cast<volatile unsigned long long*>(&ws->pair);
-      const uint32_t c[2] = {(uint32_t)(pr >> 32), (uint32_t)pr};
-      const unsigned int carry = ws->carry;
-      unsigned int seen = carry;
-      for (int t = 0; t < 2; ++t) {
-        if (c[t] == 0u) break;
-        if (seen < 2 && p.coord_mode == YOLO1_COORD_REFERENCE) {
-          // v1Loss.py:101 `[:2]`: this object is one of the first two of the call -> plain form
-          const int64_t q = (int64_t)(0xFFFFFFFFu - c[t]);
-          const E* zq = reinterpret_cast<const E*>(p.pred) + cell_offset(p.ps, q, p.S);
-          GlobIn<E> P{zq, p.ps[3], p.logits != 0};
-          GlobOut<E> G{HAS_GRAD ? reinterpret_cast<E*>(p.grad) + cell_offset(p.gs, q, p.S) : nullptr, p.gs[3], zq,
-                       p.ps[3], p.logits != 0};
-          CellSums d = {0.f, 0.f, 0.f, 0.f};
-          if (p.list_mode) {
-            cell_generic<HAS_GRAD, true>(P, list_targetS(p, q), G, p, d);
-          } else {
-            GlobIn<float> T{p.target + cell_offset(p.ts, q, p.S), p.ts[3], false};
-            cell_generic<HAS_GRAD, true>(P, T, G, p, d);
-          }
-          t4[0] += (double)d.loc;
-        }
-        ++seen;
-      }
-      double acc[4];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    t4[0] += fixloc[0] + fixloc[1];
+    const unsigned int seen = carry + (c[0] != 0u ? 1u : 0u) + (c[1] != 0u ? 1u : 0u);
+    double acc[4];
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        acc[t] = ws->acc[t] + t4[t];
-        ws->acc[t] = acc[t];
-      }
-      ws->carry = seen > 2 ? 2 : seen;
-      ws->pair = 0ull;
-      ws->ticket = 0u;
-      if (p.last_chunk) {
-        // v1Loss.py:104-108: the four logged components and the total, each / batch_size
-        const double ib = (double)p.inv_bs;
-        p.terms[0] = (float)(acc[0] * ib);
-        p.terms[1] = (float)(acc[1] * ib);
-        p.terms[2] = (float)(acc[2] * ib);
-        p.terms[3] = (float)(acc[3] * ib);
-        p.terms[4] = (float)(((double)p.lc * acc[0] + acc[1] + (double)p.ln * acc[2] + acc[3]) * ib);
-      }
+    for (int t = 0; t < 4; ++t) {
+      acc[t] = ws->acc[t] + t4[t];
+      ws->acc[t] = acc[t];
+    }
+    ws->carry = seen > 2 ? 2 : seen;
+    ws->pair = 0ull;
+    ws->ticket = 0u;
+    if (p.last_chunk) {
+      // v1Loss.py:104-108: the four logged components and the total, each / batch_size
+      const double ib = (double)p.inv_bs;
+      p.terms[0] = (float)(acc[0] * ib);
+      p.terms[1] = (float)(acc[1] * ib);
+      p.terms[2] = (float)(acc[2] * ib);
+      p.terms[3] = (float)(acc[3] * ib);
+      p.terms[4] = (float)(((double)p.lc * acc[0] + acc[1] + (double)p.ln * acc[2] + acc[3]) * ib);
     }
   }
 }
