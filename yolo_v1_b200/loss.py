@@ -6,6 +6,7 @@ arithmetic runs in libyolo1_b200.so (yolo_v1_b200/csrc/loss.cu).
 are: `lossLayer = YOLOLossV1(batch_size, S, B, clsN, lambda_coord, lambda_noobj, _logger=..., _vis=...)`,
 `loss = lossLayer(pred, target); loss.backward()`.
 """
+import contextlib
 import ctypes
 
 import torch
@@ -18,6 +19,7 @@ __all__ = ["YOLOLossV1", "yolo_loss_fused", "yolo_loss_from_objects", "scale_gra
 
 _COORD_MODES = {"reference": _lib.COORD_REFERENCE, "paper": _lib.COORD_PAPER}
 TERM_NAMES = ("location", "contain", "not_contain", "classify", "total")
+_WS_BYTES = None
 
 
 def _dtype_code(t):
@@ -63,28 +65,36 @@ def yolo_loss_fused(pred, target, batch_size, S=None, B=2, C=20, l_coord=5.0, l_
     if target.dtype != torch.float32:
         target = target.float()
     L = _lib.lib()
-    with torch.cuda.device(dev):
+    # (a small call is shorter than this function: the device guard is entered only when the tensors live on another
+    #  device than the current one, and the constant workspace size is asked for once)
+    guard = torch.cuda.device(dev) if torch.cuda.current_device() != dev.index else contextlib.nullcontext()
+    with guard:
         grad = None
         if want_grad:
             grad = out_grad if out_grad is not None else torch.empty_like(pred)
             if grad.shape != pred.shape or grad.dtype != pred.dtype or grad.device != dev:
                 raise ValueError("out_grad must match pred in shape, dtype and device")
         terms = out_terms if out_terms is not None else torch.empty(5, dtype=torch.float32, device=dev)
-        ws_bytes = int(L.yolo1_loss_workspace_bytes(N, S, B, C))
+        global _WS_BYTES
+        if _WS_BYTES is None:
+            _WS_BYTES = int(L.yolo1_loss_workspace_bytes(N, S, B, C))    # independent of the call (include/yolo1_b200.h)
+        ws_bytes = _WS_BYTES
         ws = workspace if workspace is not None else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         if ws.numel() * ws.element_size() < ws_bytes:
             raise ValueError("workspace too small: need %d bytes" % ws_bytes)
+        gstr = _lib.strides4(grad) if grad is not None else None
         common = (pred.data_ptr(), _lib.strides4(pred), _dtype_code(pred),
                   target.data_ptr(), _lib.strides4(target),
-                  grad.data_ptr() if grad is not None else None,
-                  _lib.strides4(grad) if grad is not None else None,
+                  grad.data_ptr() if grad is not None else None, gstr,
                   terms.data_ptr(), N, S, B, C, float(l_coord), float(l_noobj), 1.0 / float(batch_size),
                   _COORD_MODES[coord_mode], ws.data_ptr(), ws.numel() * ws.element_size())
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         if from_logits:
-            rc = L.yolo1_loss_fwd_bwd_logits(*common, _stream_ptr(dev))
+            rc = L.yolo1_loss_fwd_bwd_logits(*common, stream)
         else:
-            rc = L.yolo1_loss_fwd_bwd_ex(*common, int(variant), _stream_ptr(dev))
-        _lib.check(rc, "yolo1_loss_fwd_bwd")
+            rc = L.yolo1_loss_fwd_bwd_ex(*common, int(variant), stream)
+        if rc != 0:
+            _lib.check(rc, "yolo1_loss_fwd_bwd")
     return terms[4], grad, terms
 
 
