@@ -686,6 +686,12 @@ def main():
                                   "GPU, S=7, B=2, C=20, thresh 0.1, IoU 0.5, pred~U(0,1); L2 flushed between "
                                   "timed iterations", "tie_redrawn_images": redrawn,
                       "mean_candidates": float(cand.mean()), "mean_kept": float(cnts.float().mean().item())}}
+    # the same batch with per-class suppression (north_star wording; the reference's decoder is class-agnostic)
+    ms = max_over_ranks(time_device(lambda: y.decode_nms_batched(dpred, DEC_THRESH, DEC_IOU, class_agnostic=False,
+                                                                 out=outs), dsteps))
+    dec["per_class_nms"] = {"value": N_DEC * world / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
+                            "note": "same 4096 images, only boxes of the same class suppress each other; L2 warm"}
+    y.decode_nms_batched(dpred, DEC_THRESH, DEC_IOU, out=outs)      # restore the class-agnostic outputs (parity gate)
     # larger batches of the same workload (steady state: no launch ramp / tail), and the S=14 grid of train.py:41
     for tag, s_, n_ in (("s7_n65536", 7, 65536), ("s14_n16384", 14, 16384)):
         bp = synth.make_decode_inputs(n_, s_, seed=77 + rank, device=dev)

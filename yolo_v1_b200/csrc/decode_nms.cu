@@ -243,12 +243,28 @@ __device__ __forceinline__ SlotEval eval_slot(const DecodeParams& p, const Smem&
     // propagates NaN: the value is carried by a NaN-propagating max (a NaN class score makes the slot's score NaN and
     // `> thresh` drops it, so the index of such a slot is never used); the index follows the `>` of finite scans.
     const int half = (C + 1) >> 1, c0 = b ? half : 1, c1 = b ? C : half;
-    best_p = b ? -INFINITY : P[5 * B];
-    best_c = b ? half : 0;
-    for (int c = c0; c < c1; ++c) {
-      const float v = P[5 * B + c];
-      if (v > best_p) best_c = c;
-      best_p = fmax_nan(best_p, v);
+    if ((C & 3) == 0 && !((5 * B) & 1)) {
+      // two class scores per 64-bit shared load (both halves start at an even channel: 8-byte aligned).  Starting
+      // from -inf with a strict `>` keeps the first arg-max: an all -inf half keeps its first index.
+      const float2* P2 = reinterpret_cast<const float2*>(P + 5 * B + (b ? half : 0));
+      best_p = -INFINITY;
+      best_c = b ? half : 0;
+      for (int j = 0; j < (half >> 1); ++j) {
+        const float2 v = P2[j];
+        const int c = (b ? half : 0) + 2 * j;
+        if (v.x > best_p) best_c = c;
+        best_p = fmax_nan(best_p, v.x);
+        if (v.y > best_p) best_c = c + 1;
+        best_p = fmax_nan(best_p, v.y);
+      }
+    } else {
+      best_p = b ? -INFINITY : P[5 * B];
+      best_c = b ? half : 0;
+      for (int c = c0; c < c1; ++c) {
+        const float v = P[5 * B + c];
+        if (v > best_p) best_c = c;
+        best_p = fmax_nan(best_p, v);
+      }
     }
     const float op = __shfl_xor_sync(0xffffffffu, best_p, 1);
     const int oc = __shfl_xor_sync(0xffffffffu, best_c, 1);
@@ -921,20 +937,21 @@ __device__ __forceinline__ void decode_nms_image(const DecodeParams& p) {
   }
   const int cand = decode_phase<SMALL>(p, sm);
   const int kept = cand > 0 ? nms_phase<SMALL>(sm, cand, p) : 0;
-  for (int t = threadIdx.x; t < kept; t += blockDim.x) {
-    const int src = sm.keep[t], e = sm.sidx[src];
+  // kept detections in descending score order, rows beyond the count zero; streaming stores (written once, read by
+  // another kernel or the host: no reason to keep the lines in L2 ahead of the next kernel's traffic)
+  for (int t = threadIdx.x; t < p.max_n; t += blockDim.x) {
     const int64_t dst = n * p.max_n + t;
-    reinterpret_cast<float4*>(p.out_boxes)[dst] = sm.box[e];
-    p.out_scores[dst] = sm.score[e];
-    p.out_cls[dst] = sm.cls[e];
-    if (p.keep) p.keep[dst] = e;
-  }
-  for (int t = kept + threadIdx.x; t < p.max_n; t += blockDim.x) {  // rows beyond the count are zero
-    const int64_t dst = n * p.max_n + t;
-    reinterpret_cast<float4*>(p.out_boxes)[dst] = make_float4(0.f, 0.f, 0.f, 0.f);
-    p.out_scores[dst] = 0.f;
-    p.out_cls[dst] = 0;
-    if (p.keep) p.keep[dst] = 0;
+    float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+    float sc = 0.f;
+    int cl = 0, e = 0;
+    if (t < kept) {
+      e = sm.sidx[sm.keep[t]];
+      bx = sm.box[e], sc = sm.score[e], cl = sm.cls[e];
+    }
+    __stcs(reinterpret_cast<float4*>(p.out_boxes) + dst, bx);
+    __stcs(p.out_scores + dst, sc);
+    __stcs(p.out_cls + dst, cl);
+    if (p.keep) __stcs(p.keep + dst, e);
   }
   if (threadIdx.x == 0) {
     p.out_counts[n] = kept;
