@@ -5,12 +5,12 @@
 // exactly like the reference's ATen CPU ops, so candidates, scores and keep lists are bit-exact.
 //
 // One CTA per image; an image's candidates never leave shared memory in the fused kernel:
-//   load   : the image's S*S*D values -> shared (coalesced)
+//   load   : the image's S*S*D values -> shared (dense fp32: one bulk (TMA) copy per image; else coalesced loads)
 //   decode : per (cell, slot) candidate test, class arg-max (the two slots of a cell share the scan), score,
 //            `double(score) > thresh`, order-preserving compaction (ballot + prefix) = emission order; the image's
 //            maximum confidence rides on the same barrier (it only matters when no confidence exceeds 1e-4)
-//   sort   : exact rank (score descending, emission index ascending) by a counting sort into 256 score buckets and a
-//            comparison inside the bucket only: O(n) instead of the n^2 compares of a rank-by-counting
+//   sort   : exact rank (score descending, emission index ascending).  Large grids: a counting sort into 256 score
+//            buckets and a comparison inside the bucket only, O(n); 7x7 grids: rank by counting (no dependent chain)
 //   mask   : suppression bit-matrix.  IoU <= min(area) / max(area), so a pair whose areas differ by more than
 //            1 / thr cannot die: a second counting sort (area buckets, 8 per octave) puts every box next to the only
 //            partners that can matter -- a third of all pairs at thr = 0.5 -- and those are dealt out to the threads
