@@ -72,8 +72,9 @@ YOLO1_API size_t yolo1_loss_workspace_bytes(int64_t N, int S, int B, int C);
  * grad must not overlap pred or target (the row-slice fix-up re-reads two cells of pred after the streaming pass).
  * Fast paths: contiguous [N,S,S,30] tensors or the permuted NCHW view, B = 2, C = 20, 16-byte aligned bases; any
  * other strides / alignment / (B, C) take the strided one-thread-per-cell kernel (same results, ~3x slower).
- * Calls of up to 16 384 cells (train.py:38-41 trains with 12 x 14 x 14 = 2 352) run as ONE 8-CTA cluster launch
- * that resolves the `[:2]` rule before evaluating any cell and does not touch the workspace (loss_small.cu).
+ * Small calls (train.py:38-41 trains with 12 x 14 x 14 = 2 352 cells; up to 7 360 fp32 cells of the two fast layouts,
+ * 2 048 cells of any other) run as ONE 8-CTA cluster launch that resolves the `[:2]` rule before evaluating any cell
+ * and does not touch the workspace (loss_small.cu).
  * N * S * S must be below 2^32 - 1 per call.
  */
 YOLO1_API int yolo1_loss_fwd_bwd(const void* pred, const int64_t pred_strides[4], int pred_dtype,
@@ -88,8 +89,11 @@ YOLO1_API int yolo1_loss_fwd_bwd(const void* pred, const int64_t pred_strides[4]
  * (0 = the default yolo1_loss_fwd_bwd uses; 1, 2, 3, 5, 8, 13 = other tile-cells x input-stages x output-buffers
  * shapes, see loss_nhwc.cu launch_tma_variant; 20 = force the warp-specialised kernel for a channel-planar view;
  * < 0 = force the strided one-thread-per-cell kernel that also serves non-contiguous views; 30 = force the
- * small-call cluster kernel (YOLO1_ERR_UNSUPPORTED above 16 384 cells); 31 = the default streaming shape even for a
- * small call).  Same results for every variant up to summation order.
+ * small-call cluster kernels (YOLO1_ERR_UNSUPPORTED when the call does not fit them: 7 360 fp32 NHWC cells resident,
+ * 2 048 cells otherwise); 31 = the default streaming shape even for a small call; 40 / 41 / 42 = the sector-read
+ * ("confidence first") kernel for fp32 NHWC tensors with 128 / 64 / 256 cells per tile -- an experiment that moves the
+ * same DRAM bytes as the dense stream, see profiles/ncu_sparse_r2.md; 50 = force the confidence-first kernel for the
+ * permuted NCHW view, 51 = force the dense planar kernels).  Same results for every variant up to summation order.
  */
 YOLO1_API int yolo1_loss_fwd_bwd_ex(const void* pred, const int64_t pred_strides[4], int pred_dtype,
                           const float* target, const int64_t target_strides[4],
