@@ -286,3 +286,77 @@ def test_area_pruning_never_skips_a_pair_that_dies():
             check(thr, big, small)
             check(thr, small, big)
     assert _area_skip(0.5) == 10 and _area_skip(1.0) == 2      # a little over one octave at 0.5; neighbours only at 1
+
+
+def test_autotune_zero_copy_picks_the_fastest_mode_for_all_ranks():
+    """yolo_v1_b200.host.autotune_zero_copy: every mode is timed after a barrier, the per-rank time goes through
+    reduce_max (so all ranks see the same table and pick the same mode), the context is left in the winning mode."""
+    import time
+    from yolo_v1_b200 import host as yhost
+
+    class FakeCtx:
+        def __init__(self, cost):
+            self.cost, self.mode, self.calls = cost, None, []
+
+        def set_zero_copy(self, m):
+            self.mode = m
+
+        def loss(self, pred, target, batch_size, out_grad=None):
+            self.calls.append(self.mode)
+            time.sleep(self.cost[self.mode])
+
+    events = []
+    ctx = FakeCtx({0: 0.004, 1: 0.002, 2: 0.001, 4: 0.003})
+    # this rank finds mode 2 fastest, but another rank (simulated by reduce_max) is slow in mode 2: the job-wide pick
+    # must follow the maximum over the ranks
+    slow_elsewhere = {2: 50.0}
+    best, table = yhost.autotune_zero_copy(
+        ctx, None, None, None, 8, modes=(2, 1, 4, 0), repeats=2,
+        barrier=lambda: events.append(("barrier", ctx.mode)),
+        reduce_max=lambda ms: max(ms, slow_elsewhere.get(ctx.mode, 0.0)))
+    assert best == 1 and ctx.mode == 1 and set(table) == {0, 1, 2, 4} and table[2] == 50.0
+    assert [m for _, m in events] == [2, 1, 4, 0]                      # one barrier per mode, before its timed loop
+    assert ctx.calls.count(2) == 3 and ctx.calls.count(0) == 3         # one warm-up + `repeats` timed calls per mode
+    with yhost.near_gpu(0) as n:                                        # no GPU / no sysfs answer: a no-op
+        assert n.cpus is None or len(n.cpus) > 0
+
+
+def test_staged_reference_archive_is_byte_identical_and_loads(tmp_path):
+    """oracle/stage_reference.py packs the reference's two hot-path modules into oracle/_ref/reference_hot_path.zip for
+    the GPU box; oracle/ref_loader.py must be able to run the reference from that archive alone, and the members must
+    be the mounted files byte for byte.  (Build container only: needs the reference mount.)"""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    import zipfile
+    ref = "/root/reference"
+    if not os.path.isfile(os.path.join(ref, "v1Loss.py")):
+        pytest.skip("reference tree not mounted")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(y.__file__)))
+    from oracle import stage_reference
+    assert stage_reference.stage() and os.path.isfile(stage_reference.ARCHIVE)
+    with zipfile.ZipFile(stage_reference.ARCHIVE) as z:
+        assert sorted(z.namelist()) == ["utils/utils.py", "v1Loss.py"]
+        for name in z.namelist():
+            assert hashlib.sha256(z.read(name)).hexdigest() == hashlib.sha256(open(os.path.join(ref, name), "rb").read()).hexdigest()
+    code = """
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from oracle import ref_loader, oracle as O
+from yolo_v1_b200 import synth
+assert ref_loader.REF_ROOT.endswith("reference_hot_path.zip"), ref_loader.REF_ROOT
+Loss, U = ref_loader.load_reference()
+pred, target = synth.make_loss_inputs(4, 7, seed=3, p_obj=0.2)
+p = pred.clone().requires_grad_(True)
+with ref_loader.quiet():
+    l = Loss(4, 7, 2, 20, 5., .5, _device='cpu')(p, target); l.backward()
+    k = U.nms(torch.tensor([[0., 0., 1., 1.], [0.1, 0., 1.1, 1.], [3., 3., 4., 4.]]), torch.tensor([.9, .8, .7]), 0.5)
+t, g = O.loss(pred.numpy(), target.numpy(), batch_size=4)
+assert abs(float(l) - float(t[4])) <= 2e-6 * abs(float(l)) and np.abs(g - p.grad.numpy()).max() <= 2e-6 * np.abs(g).max()
+assert k.tolist() == [0, 2]
+print("ok")
+""" % root
+    env = dict(os.environ, YOLO1_REFERENCE_ROOT=stage_reference.ARCHIVE, PYTHONDONTWRITEBYTECODE="1")
+    r = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
