@@ -24,12 +24,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--no-fuse-head", action="store_true")
     ap.add_argument("--backbone", default="resnet50", choices=["resnet50", "densenet121"])
+    ap.add_argument("--graph-loss", action="store_true", help="loss kernel + terms all-reduce replayed as one CUDA graph")
     a = ap.parse_args()
     rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(lr)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
-    ts = TrainStep(S=a.S, batch_size=a.batch, device="cuda:%d" % lr, ddp=world > 1, fuse_head=not a.no_fuse_head, backbone=a.backbone)
+    ts = TrainStep(S=a.S, batch_size=a.batch, device="cuda:%d" % lr, ddp=world > 1, fuse_head=not a.no_fuse_head, backbone=a.backbone,
+                   graph_loss=a.graph_loss)
     images = torch.randn(a.batch, 3, 448, 448, device="cuda").to(memory_format=torch.channels_last)
     _, target = synth.make_loss_inputs(a.batch, a.S, seed=1 + rank, device="cuda")
     for _ in range(a.warmup):
@@ -48,12 +50,13 @@ def main():
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         pred = ts.net(images)
     pred = pred.detach().requires_grad_(True)
+    loss_call = ts.graphed if a.graph_loss else ts.loss
     for _ in range(3):
-        ts.loss(pred, target).backward()
+        loss_call(pred, target).backward()
     l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0.record()
     for _ in range(50):
-        ts.loss(pred, target).backward()
+        loss_call(pred, target).backward()
     l1.record()
     torch.cuda.synchronize()
     loss_ms = l0.elapsed_time(l1) / 50
@@ -64,8 +67,9 @@ def main():
         print(json.dumps({"config": "config5: %s-YOLOv1 448x448 bf16 %s train step, S=%d, batch %d per GPU, fused loss%s" %
                           (a.backbone, "DDP x%d" % world if world > 1 else "single GPU", a.S, a.batch, "" if a.no_fuse_head else " + fused sigmoid head"),
                           "images_per_s": a.batch * world / (float(t) * 1e-3), "ms_per_step": float(t), "n_gpus": world,
-                          "loss_fwd_bwd_ms": loss_ms, "loss_share_of_step": loss_ms / float(t), "loss": float(loss),
+                          "loss_fwd_bwd_ms": loss_ms, "graph_loss": bool(a.graph_loss), "loss_share_of_step": loss_ms / float(t), "loss": float(loss),
                           "pred_dtype": str(pred.dtype), "pred_strides": list(pred.stride())}))
+    ts.close()      # a graph that captured the all-reduce goes before the process group
     if world > 1:
         dist.destroy_process_group()
 
