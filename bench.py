@@ -702,6 +702,33 @@ def main():
         dec[tag] = {"value": n_ * world / (ms * 1e-3), "unit": "images/s", "ms_per_step": ms,
                     "note": "inputs larger than L2"}
         del bp, bo
+    # config 2 as an evaluation loop runs it: a stream of 4096-image batches, 16 distinct ones (385 MB of predictions +
+    # 180 MB of outputs > 126 MB L2, so every launch reads HBM), the 16 launches captured into one CUDA graph and
+    # replayed inside ONE event pair -- no flush kernel and no event / host gap between launches.  `value` above stays
+    # the lone cold launch (round 1's definition); this is the same kernel on the same batch size, back to back.
+    nbat = 16
+    bps = [dpred] + [synth.make_decode_inputs(N_DEC, S_DEC, seed=900 + 16 * rank + i, device=dev) for i in range(nbat - 1)]
+    bos = [tuple(torch.empty_like(o) for o in outs) for _ in range(nbat)]
+
+    def eval_loop():
+        for bp_, bo_ in zip(bps, bos):
+            y.decode_nms_batched(bp_, DEC_THRESH, DEC_IOU, out=bo_)
+
+    eval_loop()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    gdec = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gdec, stream=side, capture_error_mode="thread_local"):
+        eval_loop()
+    torch.cuda.current_stream().wait_stream(side)
+    ms = max_over_ranks(time_device(gdec.replay, max(2, dsteps // 4))) / nbat
+    same = all(torch.equal(a_, b_) for a_, b_ in zip(bos[0], outs))
+    dec["stream_of_batches"] = {"value": N_DEC * world / (ms * 1e-3), "unit": "images/s", "ms_per_batch": ms,
+                                "batches": nbat, "first_batch_equals_lone_launch": bool(same),
+                                "note": "16 distinct 4096-image batches (inputs + outputs 565 MB > L2), the 16 launches "
+                                        "replayed as one CUDA graph inside one event pair"}
+    del gdec, bps, bos
     if not args.no_e2e:
         dh = dpred_h.pin_memory()
         dctx = y.HostContext(S_DEC, B, C, device=local_rank)

@@ -33,6 +33,15 @@ namespace {
 // (rolled 11.18).  The kernel is sensitive to its code size (ncu: no_instruction stalls), not only to its
 // instruction count.
 constexpr int kMaxCand = 1024;
+#ifndef YOLO1_DECODE_PERSIST
+#define YOLO1_DECODE_PERSIST 0
+#endif
+#ifndef YOLO1_DECODE_PERSIST_SPLIT
+#define YOLO1_DECODE_PERSIST_SPLIT 1
+#endif
+#ifndef YOLO1_DECODE_L2PF
+#define YOLO1_DECODE_L2PF 0
+#endif
 constexpr int kKeepA = 64, kKeepB = 128;            // slots of Smem::misc (sweep): the two copies of the kept-set words
 constexpr int kNotes = 96, kKmin = 97, kKmax = 98, kRankSum = 99, kBar = 100;   // ... (nms_phase): unsettled-pair count, score-key
                                                                       // range, rank checksum
@@ -106,20 +115,33 @@ struct Smem {
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-__host__ __device__ inline size_t smem_layout(unsigned char* base, int img_floats, int max_n, Smem* s) {
+// split: the persistent small-grid kernel (decode_nms_persistent_kernel) loads image k+1 while image k is in its
+// NMS phase, so the arrays of that phase must not lie over the image: mask and akey follow the image region, tkey
+// takes the score-bucket half of `hist` (unused by the small-grid phases; 512 bytes >= 4 max_n for max_n <= 128), and
+// bidx / notes (large-grid phases only) do not exist.
+__host__ __device__ inline size_t smem_layout(unsigned char* base, int img_floats, int max_n, Smem* s,
+                                              bool split = false) {
   const int W = (max_n + 31) / 32;
   const size_t mask_bytes = align16((size_t)max_n * W * 4), n4 = align16((size_t)max_n * 4);
   size_t region = (size_t)img_floats * 4 + (img_floats ? 16 : 0);   // + the bulk load's alignment slack
   const size_t after = mask_bytes + n4 /*bidx*/ + 2 * n4 /*notes*/ + n4 /*tkey*/ + n4 /*akey*/;
-  if (after > region) region = after;
-  if (s) {
-    s->img = reinterpret_cast<float*>(base), s->mask = reinterpret_cast<uint32_t*>(base);
-    s->bidx = reinterpret_cast<int32_t*>(base + mask_bytes);
-    s->notes = reinterpret_cast<uint32_t*>(base + mask_bytes + n4);
-    s->tkey = reinterpret_cast<uint32_t*>(base + mask_bytes + 3 * n4);
-    s->akey = reinterpret_cast<uint32_t*>(base + mask_bytes + 4 * n4);
-  }
+  if (!split && after > region) region = after;
   size_t off = align16(region);
+  if (s) {
+    s->img = reinterpret_cast<float*>(base);
+    if (split) {
+      s->mask = reinterpret_cast<uint32_t*>(base + off);
+      s->akey = reinterpret_cast<uint32_t*>(base + off + mask_bytes);
+      s->bidx = nullptr, s->notes = nullptr;
+    } else {
+      s->mask = reinterpret_cast<uint32_t*>(base);
+      s->bidx = reinterpret_cast<int32_t*>(base + mask_bytes);
+      s->notes = reinterpret_cast<uint32_t*>(base + mask_bytes + n4);
+      s->tkey = reinterpret_cast<uint32_t*>(base + mask_bytes + 3 * n4);
+      s->akey = reinterpret_cast<uint32_t*>(base + mask_bytes + 4 * n4);
+    }
+  }
+  if (split) off += mask_bytes + n4;
   if (s) {
     s->sbox = reinterpret_cast<float4*>(base + off);
     s->abox = reinterpret_cast<float4*>(base + off);
@@ -140,6 +162,7 @@ __host__ __device__ inline size_t smem_layout(unsigned char* base, int img_float
   if (s) s->keep = reinterpret_cast<int32_t*>(base + off);
   off += n4;
   if (s) s->hist = reinterpret_cast<uint32_t*>(base + off);
+  if (s && split) s->tkey = reinterpret_cast<uint32_t*>(base + off);
   off += kNB * 4;
   if (s) s->misc = reinterpret_cast<int32_t*>(base + off);
   off += 160 * 4;
@@ -929,6 +952,13 @@ __device__ __forceinline__ void decode_nms_image(const DecodeParams& p) {
         mbar_fence_init();
         mbar_arrive_expect_tx(bar, bytes);
         bulk_g2s(raw, src - mis, bytes, bar, policy_evict_first());
+#if YOLO1_DECODE_L2PF
+        // the image of the CTA that will take this CTA's place (one wave = 148 SMs x 16 CTAs later): into L2 now
+        if (n + YOLO1_DECODE_L2PF < p.n_images - 1)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src - mis + (int64_t)YOLO1_DECODE_L2PF * img_bytes),
+                       "r"(bytes - 16u)
+                       : "memory");
+#endif
       }
       sm.img = reinterpret_cast<float*>(raw + mis);
       nms_prepare<SMALL>(sm);
@@ -964,6 +994,98 @@ __device__ __forceinline__ void decode_nms_image(const DecodeParams& p) {
     if (p.cand_counts) p.cand_counts[n] = cand;
   }
 }
+
+#if YOLO1_DECODE_PERSIST
+// ---- measured and NOT shipped (round 2; -DYOLO1_DECODE_PERSIST=1 builds it, tools/build_decode_variant.sh) ----------
+// VERDICT r1 item 5 asked for a persistent grid that prefetches the next image.  On B200 (tools/compare_decode_libs.py,
+// one box, M images/s at S=7 N=4096 / N=65536, profiles/decode_persist_r2.log): one CTA per image 133 / 190;
+// persistent with the split layout (14 CTAs per SM) 105 / 147; persistent over the shared layout, next image issued
+// behind the sweep (16 CTAs per SM) 105 / 150.  The image loop keeps the loop state and the layout's addresses alive
+// across all phases: at the 40 registers that 16 (or 14) resident CTAs allow that is 150 bytes of spills inside a
+// kernel that is bound by instruction issue, and it costs more than the hidden load latency returns.  An L2 prefetch
+// of the image one wave ahead (YOLO1_DECODE_L2PF=2368, one instruction per CTA) also loses: 125 / 189.
+// Persistent small-grid form (dense fp32 input, up to 128 candidates): the grid is what fits the machine at once and
+// CTA b takes images b, b + grid, b + 2 grid, ...  The image region is not shared with the NMS arrays (split layout),
+// so the bulk load of the CTA's NEXT image is issued the moment the decode phase has read the current one and lands
+// while rank, pair loop, sweep and the output stores run: the load latency a fresh CTA would sit through at its
+// start (and the block scheduler's relaunch) is paid once per CTA instead of once per image.  Cost: 1 968 bytes more
+// shared memory per CTA, 14 resident CTAs per SM instead of 16.
+// image n as a bulk copy: the source rounded out to 16-byte bounds (see decode_nms_image); false for the one image
+// whose rounded copy would end beyond the tensor
+__device__ __forceinline__ bool bulk_shape(const DecodeParams& p, uint32_t img_bytes, int n, uint32_t& mis,
+                                           uint32_t& bytes) {
+  const uintptr_t src = reinterpret_cast<uintptr_t>(p.pred) + (uint64_t)n * img_bytes;
+  mis = (uint32_t)(src & 15u);
+  bytes = (img_bytes + mis + 15u) & ~15u;
+  return !(n == (int)p.n_images - 1 && bytes > img_bytes + mis);
+}
+__device__ __forceinline__ void bulk_issue(const DecodeParams& p, uint32_t img_bytes, int n, unsigned char* raw,
+                                           uint64_t* bar) {   // one thread
+  uint32_t mis, bytes;
+  if (!bulk_shape(p, img_bytes, n, mis, bytes)) return;
+  mbar_arrive_expect_tx(bar, bytes);
+  bulk_g2s(raw, reinterpret_cast<const unsigned char*>(p.pred) + (uint64_t)n * img_bytes - mis, bytes, bar,
+           policy_evict_first());
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(96, SPLIT ? 14 : 16) decode_nms_persistent_kernel(const __grid_constant__ DecodeParams p) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  Smem sm;
+  smem_layout(raw, p.S * p.S * (5 * p.B + p.C), p.max_n, &sm, SPLIT);
+  const uint32_t img_bytes = (uint32_t)(p.S * p.S * (5 * p.B + p.C)) * 4u;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm.misc + kBar);
+  const int n_images = (int)p.n_images;   // one CTA per image in the other form: the count fits an int
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+    bulk_issue(p, img_bytes, (int)blockIdx.x, raw, bar);
+  }
+  uint32_t phase = 0;
+  for (int n = blockIdx.x; n < n_images; n += gridDim.x) {
+    nms_prepare<true>(sm);
+    __syncthreads();            // first trip: the barrier is initialised before anyone polls it
+    uint32_t mis, bytes;
+    if (bulk_shape(p, img_bytes, n, mis, bytes)) {
+      sm.img = reinterpret_cast<float*>(raw + mis);
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+    } else {
+      sm.img = reinterpret_cast<float*>(raw);
+      load_image<float>(p, n, sm.img);
+      __syncthreads();
+    }
+    const int cand = decode_phase<true>(p, sm);   // ends behind a CTA barrier: nobody reads the image any more
+    if (SPLIT && threadIdx.x == 0 && n + (int)gridDim.x < n_images) bulk_issue(p, img_bytes, n + gridDim.x, raw, bar);
+    const int kept = cand > 0 ? nms_phase<true>(sm, cand, p) : 0;
+    // !SPLIT: the image region holds the suppression matrix until the sweep is over; the next image can only travel
+    // behind the output stores (generic-proxy writes to the region happened before: order them before the copy)
+    if (!SPLIT && threadIdx.x == 0 && n + (int)gridDim.x < n_images) {
+      fence_async_smem();
+      bulk_issue(p, img_bytes, n + gridDim.x, raw, bar);
+    }
+    for (int t = threadIdx.x; t < p.max_n; t += blockDim.x) {
+      const int64_t dst = (int64_t)n * p.max_n + t;
+      float4 bx = make_float4(0.f, 0.f, 0.f, 0.f);
+      float sc = 0.f;
+      int cl = 0, e = 0;
+      if (t < kept) {
+        e = sm.sidx[sm.keep[t]];
+        bx = sm.box[e], sc = sm.score[e], cl = sm.cls[e];
+      }
+      __stcs(reinterpret_cast<float4*>(p.out_boxes) + dst, bx);
+      __stcs(p.out_scores + dst, sc);
+      __stcs(p.out_cls + dst, cl);
+      if (p.keep) __stcs(p.keep + dst, e);
+    }
+    if (threadIdx.x == 0) {
+      p.out_counts[n] = kept;
+      if (p.cand_counts) p.cand_counts[n] = cand;
+    }
+    __syncthreads();            // the candidate arrays are free for the next image
+  }
+}
+#endif  // YOLO1_DECODE_PERSIST
 
 template <typename E, bool SMALL>
 __global__ void decode_nms_kernel(const __grid_constant__ DecodeParams p) {
@@ -1064,6 +1186,24 @@ int launch(const DecodeParams& p, int64_t N, int img_floats, cudaStream_t stream
   KERN<<<(unsigned)N, block_threads(p.max_n), smem, stream>>>(p);
   return (int)cudaGetLastError();
 }
+
+#if YOLO1_DECODE_PERSIST
+int launch_persistent(const DecodeParams& p, int64_t N, int img_floats, cudaStream_t stream) {
+  constexpr bool kSplit = YOLO1_DECODE_PERSIST_SPLIT;
+  const size_t smem = smem_layout(nullptr, img_floats, p.max_n, nullptr, kSplit);
+  static KernelPrep prep;
+  int sms = kNumSMs, per_sm = 1;
+  if (int rc = prepare_kernel(prep, decode_nms_persistent_kernel<kSplit>, 96, smem, true, &sms, &per_sm)) return rc;
+  int64_t grid = (int64_t)sms * per_sm;
+  if (grid > N) grid = N;
+  decode_nms_persistent_kernel<kSplit><<<(unsigned)grid, 96, smem, stream>>>(p);
+  return (int)cudaGetLastError();
+}
+// YOLO1_DECODE_PERSIST = 1: every eligible call; = k > 1: calls of up to k * 2368 images
+inline bool persist_wanted(int64_t N) {
+  return YOLO1_DECODE_PERSIST == 1 || N <= (int64_t)YOLO1_DECODE_PERSIST * 2368;
+}
+#endif
 
 int check_decode_args(const void* pred, const int64_t st[4], int dtype, int64_t N, int S, int B, int C) {
   if (!st || N < 0 || S <= 0 || B <= 0 || C <= 0) return YOLO1_ERR_ARG;
@@ -1208,6 +1348,9 @@ int yolo1_decode_nms(const void* pred, const int64_t pred_strides[4], int pred_d
               (uintptr_t)pred % 16 == 0 && ((int64_t)S * S * Dch * 4) % 8 == 0;
   const int img = S * S * (5 * B + C);
   const bool defer = p.max_n <= 128;   // up to 128 candidates: 96-thread CTAs and the one-warp register sweep
+#if YOLO1_DECODE_PERSIST
+  if (defer && p.bulk_ok && persist_wanted(N)) return launch_persistent(p, N, img, (cudaStream_t)stream);
+#endif
   if (pred_dtype == YOLO1_DTYPE_BF16)
     return defer ? launch<decode_nms_kernel<__nv_bfloat16, true>>(p, N, img, (cudaStream_t)stream)
                  : launch<decode_nms_kernel<__nv_bfloat16, false>>(p, N, img, (cudaStream_t)stream);
