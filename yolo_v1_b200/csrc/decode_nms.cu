@@ -1004,6 +1004,8 @@ __device__ __forceinline__ void decode_nms_image(const DecodeParams& p) {
 // across all phases: at the 40 registers that 16 (or 14) resident CTAs allow that is 150 bytes of spills inside a
 // kernel that is bound by instruction issue, and it costs more than the hidden load latency returns.  An L2 prefetch
 // of the image one wave ahead (YOLO1_DECODE_L2PF=2368, one instruction per CTA) also loses: 125 / 189.
+// (Also measured: the 7x7x30 shape as compile-time constants -- 16 % fewer static instructions, 196 at N=65536 but
+//  125-130 for the lone 4096-image launch, profiles/decode_persist_r2.log; not kept.)
 // Persistent small-grid form (dense fp32 input, up to 128 candidates): the grid is what fits the machine at once and
 // CTA b takes images b, b + grid, b + 2 grid, ...  The image region is not shared with the NMS arrays (split layout),
 // so the bulk load of the CTA's NEXT image is issued the moment the decode phase has read the current one and lands
