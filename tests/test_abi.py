@@ -95,3 +95,18 @@ def test_python_surface_fails_loudly_without_gpu_or_library(lib, monkeypatch):
     monkeypatch.setattr(lib, "SO_PATH", "/nonexistent/libyolo1_b200.so")
     with pytest.raises(lib.Yolo1LibraryError):
         lib.lib()
+
+
+def test_product_package_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under yolo_v1_b200/ (Python or CUDA) may import, load or name it,
+    and there is no CPU fallback to route through."""
+    import pathlib
+    import re
+    root = pathlib.Path(__file__).resolve().parents[1] / "yolo_v1_b200"
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|oracle[/\\.](_ref|_build|oracle|ref_loader|yolo1_oracle)|libyolo1_oracle")
+    hits = []
+    for f in list(root.rglob("*.py")) + list(root.rglob("*.cu")) + list(root.rglob("*.cuh")) + list(root.rglob("Makefile")):
+        for i, line in enumerate(f.read_text(errors="replace").splitlines(), 1):
+            if pat.search(line):
+                hits.append("%s:%d: %s" % (f.relative_to(root), i, line.strip()))
+    assert not hits, "\n".join(hits)
