@@ -123,7 +123,9 @@ YOLO1_API int yolo1_loss_fwd_bwd_logits(const void* logits, const int64_t logit_
  * what yoloDataset.encoder (utils/YOLODataLoader.py:200-230) would be fed per image; the call computes exactly
  * yolo1_loss_fwd_bwd(pred, encoder(boxes, labels), ...) (or ..._logits when from_logits != 0) but reads
  * 4 bytes per cell (the index of the owning object) instead of a 120-byte target row: 248 instead of 360
- * algorithmic bytes per cell.  workspace: yolo1_loss_objects_workspace_bytes(N,S,B,C) bytes, 16-byte aligned
+ * algorithmic bytes per cell.  Contiguous fp32 calls beyond the small-call sizes read not even that: a helper warp
+ * of the streaming kernel finds the owners of the tiles ahead from the lists themselves (no pre-pass kernel, no
+ * map: 240 bytes per cell).  workspace: yolo1_loss_objects_workspace_bytes(N,S,B,C) bytes, 16-byte aligned
  * (header + per-CTA partials + the N*S*S int32 cell map).  status: device int32, 1 if a centre / label was
  * outside the grid / class range (the reference raises IndexError; such objects are skipped), else 0.
  */
@@ -136,7 +138,9 @@ YOLO1_API int yolo1_loss_fwd_bwd_objects(const void* pred, const int64_t pred_st
                                          int coord_mode, void* workspace, size_t workspace_bytes, int32_t* status,
                                          void* stream);
 
-/* Tuning twin of yolo1_loss_fwd_bwd_objects: `variant` as in yolo1_loss_fwd_bwd_ex. */
+/* Tuning twin of yolo1_loss_fwd_bwd_objects: `variant` as in yolo1_loss_fwd_bwd_ex; in addition 60 = force the
+ * form that finds the owners inside the streaming kernel (YOLO1_ERR_UNSUPPORTED where it does not apply), 61 = force
+ * the pre-pass + ownership map.  Bit-identical results either way. */
 YOLO1_API int yolo1_loss_fwd_bwd_objects_ex(const void* pred, const int64_t pred_strides[4], int pred_dtype,
                                             int from_logits, const float* boxes, const int32_t* labels,
                                             const int64_t* offsets, void* grad, const int64_t grad_strides[4],

@@ -149,3 +149,61 @@ def test_loss_from_object_lists_empty_cases():
     o_terms, o_grad = O.loss(pred.numpy(), np.zeros((5, 7, 7, 30), np.float32), batch_size=5)
     assert np.allclose(t.cpu().numpy(), o_terms, rtol=1e-5) and o_terms[0] == 0 and o_terms[3] == 0
     assert np.abs(g.cpu().numpy() - o_grad).max() <= 1e-5 * np.abs(o_grad).max()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,logits", [("f32", False), ("bf16", False), ("f32", True)])
+def test_object_list_owners_found_in_the_streaming_kernel(dtype, logits):
+    """Calls beyond the small-call sizes on contiguous tensors skip the pre-pass: warp 0 of the streaming kernel finds
+    the owner of every cell from the lists (variant 60 forces that form, 61 the pre-pass + map).  Both forms must agree
+    bit for bit, with the dense-target call on encoder(lists), and with the oracle -- including images without
+    objects, images with more objects than the 32 lanes of the pipeline, collisions, the Python -1 index, a ragged
+    last tile, and an out-of-grid object (skipped, reported through the status word)."""
+    import yolo_v1_b200 as y
+    rng = np.random.RandomState(5)
+    for S, N in [(14, 203), (7, 701), (3, 2000)]:
+        counts = rng.randint(0, 6, size=N)
+        counts[0] = 0
+        counts[5] = 45                                    # more than one warp of objects in a tile's images
+        counts[6] = 70
+        counts[N - 1] = 3                                 # objects in the ragged tail
+        offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        n_obj = int(offsets[-1])
+        boxes = rng.rand(n_obj, 4).astype(np.float32)
+        boxes[:, 2:] = boxes[:, 2:] * 0.8 + 0.05
+        boxes[1, :2] = boxes[0, :2]                       # collision: the last object in a cell wins
+        boxes[2, :2] = [0.0, 1.0]                         # Python -1 indexing / edge
+        labels = rng.randint(0, 20, size=n_obj).astype(np.int32)
+        dense = O.encode(boxes, labels, offsets, S)
+        g = torch.Generator().manual_seed(S + N)
+        pred = torch.randn(N, S, S, 30, generator=g) * 1.5 if logits else torch.rand(N, S, S, 30, generator=g) * 0.98 + 0.01
+        if dtype == "bf16":
+            pred = pred.to(torch.bfloat16)
+        pc = pred.cuda()
+        b, l, o = torch.from_numpy(boxes).cuda(), torch.from_numpy(labels).cuda(), torch.from_numpy(offsets).cuda()
+        _, g0, t0 = y.yolo_loss_from_objects(pc, b, l, o, batch_size=N, from_logits=logits, check=True)       # default
+        _, g1, t1 = y.yolo_loss_from_objects(pc, b, l, o, batch_size=N, from_logits=logits, variant=60, check=True)
+        _, g2, t2 = y.yolo_loss_from_objects(pc, b, l, o, batch_size=N, from_logits=logits, variant=61, check=True)
+        _, g3, t3 = y.yolo_loss_fused(pc, torch.from_numpy(dense).cuda(), batch_size=N, from_logits=logits)
+        assert torch.equal(g1, g2) and torch.equal(g0, g1) and torch.equal(g1, g3), (S, N, dtype, logits)
+        assert torch.equal(t1, t2) and torch.equal(t0, t1), (t1, t2)
+        assert torch.allclose(t1, t3, rtol=2e-6, atol=1e-7)
+        _, _, t4 = y.yolo_loss_from_objects(pc, b, l, o, batch_size=N, from_logits=logits, variant=60, want_grad=False)
+        assert torch.allclose(t4, t1, rtol=2e-6, atol=1e-7)
+        if not logits and dtype == "f32":
+            o_terms, o_grad = O.loss(pred.numpy(), dense, batch_size=N)
+            assert np.allclose(t1.cpu().numpy(), o_terms, rtol=1e-5)
+            assert np.abs(g1.cpu().numpy() - o_grad).max() <= 1e-5 * max(np.abs(o_grad).max(), 1e-12)
+        # an object outside the grid: skipped by both forms, IndexError with check=True (the reference's behaviour)
+        bad = boxes.copy()
+        bad[n_obj // 2, 0] = 1.5
+        bb = torch.from_numpy(bad).cuda()
+        for v in (60, 61):
+            with pytest.raises(IndexError):
+                y.yolo_loss_from_objects(pc, bb, l, o, batch_size=N, from_logits=logits, variant=v, check=True)
+        _, ga, ta = y.yolo_loss_from_objects(pc, bb, l, o, batch_size=N, from_logits=logits, variant=60, check=False)
+        _, gb, tb = y.yolo_loss_from_objects(pc, bb, l, o, batch_size=N, from_logits=logits, variant=61, check=False)
+        assert torch.equal(ga, gb) and torch.equal(ta, tb)
+    # too small for the in-kernel form: forcing it is refused, the default takes the pre-pass
+    with pytest.raises(Exception):
+        y.yolo_loss_from_objects(pc[:4], b[:0], l[:0], torch.zeros(5, dtype=torch.int64).cuda(), batch_size=4, variant=60)

@@ -214,11 +214,15 @@ int launch_generic(const LossParams& p, cudaStream_t stream) {
 // Launches one chunk of a loss call.  chunk_flags: bit 0 = first chunk (resets the workspace), bit 1 = last
 // chunk (writes terms), bit 2 = pred holds pre-sigmoid logits (fused head epilogue).  variant < 0 forces the generic kernel.  Used by the public entry points below and by
 // the host-buffer pipeline (host_ctx.cu).
-struct ObjectLists {  // non-null: targets come as object lists (cellobj prepared by object_cells_kernel)
-  const int32_t* cellobj;
+struct ObjectLists {  // non-null: targets come as object lists
+  const int32_t* cellobj;   // ownership map prepared by object_cells_kernel, or null: the streaming kernel finds the
+                            // owners itself (list_mode 2; contiguous fast path only) from offsets / status
   const float* boxes;
   const int32_t* labels;
+  const int64_t* offsets;
+  int32_t* status;
 };
+constexpr int kVariantOwnersInKernel = 60;   // objects entry point: force list_mode 2; 61 = force the pre-pass
 
 int loss_launch_chunk_impl(const void* pred, const int64_t ps[4], int pred_dtype, const float* target,
                            const int64_t ts_in[4], const ObjectLists* lists, void* grad, const int64_t gs[4],
@@ -241,7 +245,8 @@ int loss_launch_chunk_impl(const void* pred, const int64_t ps[4], int pred_dtype
   if ((uintptr_t)pred % esz || (uintptr_t)target % 4 || (grad && (uintptr_t)grad % esz) || (uintptr_t)terms % 4 ||
       (uintptr_t)workspace % 8)
     return YOLO1_ERR_ALIGN;
-  if (lists) target = reinterpret_cast<const float*>(lists->cellobj);  // a 16-byte aligned stand-in for the checks below
+  if (lists)   // a 16-byte aligned stand-in for the checks below
+    target = lists->cellobj ? reinterpret_cast<const float*>(lists->cellobj) : lists->boxes;
 
   LossParams p;
   p.pred = pred, p.target = target, p.grad = grad, p.terms = terms, p.ws = reinterpret_cast<LossWs*>(workspace);
@@ -250,9 +255,10 @@ int loss_launch_chunk_impl(const void* pred, const int64_t ps[4], int pred_dtype
   p.Sf = (float)S, p.lc = lambda_coord, p.ln = lambda_noobj, p.inv_bs = inv_batch_size;
   p.k2ln = 2.0f * lambda_noobj * inv_batch_size, p.k2 = 2.0f * inv_batch_size;
   p.coord_mode = coord_mode, p.last_chunk = (chunk_flags & 2) ? 1 : 0, p.logits = (chunk_flags & 4) ? 1 : 0;
-  p.list_mode = lists ? 1 : 0;
+  p.list_mode = lists ? (lists->cellobj ? 1 : 2) : 0;
   p.cellobj = lists ? lists->cellobj : nullptr, p.boxes = lists ? lists->boxes : nullptr;
   p.labels = lists ? lists->labels : nullptr, p.cs = (float)(1.0 / (double)S);
+  p.offsets = lists ? lists->offsets : nullptr, p.status = lists ? lists->status : nullptr;
   if (lists) p.target = nullptr;
 
   // Small single-chunk calls (train.py:38-41 trains with 12 x 14 x 14 = 2 352 cells; BASELINE config 1 is 1 568):
@@ -289,6 +295,7 @@ int loss_launch_chunk_impl(const void* pred, const int64_t ps[4], int pred_dtype
   if (fast) {
     return launch_loss_nhwc(p, bf, grad != nullptr, variant, stream);
   }
+  if (p.list_mode == 2) return YOLO1_ERR_UNSUPPORTED;   // only the kernel above searches the lists itself
   // contiguous tensors of any (B, C): the same bulk-copy pipeline with a runtime channel count
   const bool fast_any = variant >= 0 && !lists && contiguous(ps, S, D) && contiguous(ts, S, D) &&
                         (!grad || contiguous(gs, S, D)) && (uintptr_t)pred % 16 == 0 && (uintptr_t)target % 16 == 0 &&
@@ -364,6 +371,24 @@ int yolo1_loss_fwd_bwd_objects_ex(const void* pred, const int64_t pred_strides[4
   int32_t* cellobj = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) + sizeof(LossWs));
   const int64_t cells = N * S * S;
   YOLO1_CUDA_TRY(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
+  // Calls that will run the contiguous streaming kernel (same test as loss_launch_chunk_impl's `fast`, beyond the
+  // small-call sizes) skip the pre-pass and its map: warp 0 of every CTA finds the owners of the tiles ahead.
+  const int D = 5 * B + C;
+  // fp32 only: the helper warp's registers cost the bf16 kernel three of its seven resident CTAs per SM (measured:
+  // 0.419 against 0.333 ms at config-3 size), while fp32 tiles are limited by shared memory either way.
+  const bool in_kernel = (variant == 0 || variant == kVariantOwnersInKernel) && B == 2 && C == 20 && S >= 3 &&
+                         (pred_dtype == YOLO1_DTYPE_F32 || variant == kVariantOwnersInKernel) &&
+                         cells > kSmallTryCells && pred_strides && contiguous(pred_strides, S, D) &&
+                         (!grad || (grad_strides && contiguous(grad_strides, S, D))) && (uintptr_t)pred % 16 == 0 &&
+                         (!grad || (uintptr_t)grad % 16 == 0);
+  if (variant == kVariantOwnersInKernel && !in_kernel) return YOLO1_ERR_UNSUPPORTED;
+  if (variant == kVariantOwnersInKernel || variant == kVariantOwnersInKernel + 1) variant = 0;
+  if (in_kernel) {
+    const ObjectLists lists = {nullptr, boxes, labels, offsets, status};
+    return loss_launch_chunk_impl(pred, pred_strides, pred_dtype, nullptr, nullptr, &lists, grad, grad_strides, terms, N,
+                                  S, B, C, lambda_coord, lambda_noobj, inv_batch_size, coord_mode, workspace,
+                                  workspace_bytes, 3 | (from_logits ? 4 : 0), variant, s);
+  }
   if (cells > 0) {
     int G = 4096 / (S * S);   // ~16 KB of map per CTA
     G = G < 4 ? 4 : (G > 256 ? 256 : (G & ~3));   // a multiple of 4 images keeps every CTA's slice 16-byte aligned
@@ -375,7 +400,7 @@ int yolo1_loss_fwd_bwd_objects_ex(const void* pred, const int64_t pred_strides[4
                                                                       (float)(1.0 / (double)S), G, cellobj, status);
     YOLO1_CUDA_TRY(cudaGetLastError());
   }
-  const ObjectLists lists = {cellobj, boxes, labels};
+  const ObjectLists lists = {cellobj, boxes, labels, offsets, status};
   return loss_launch_chunk_impl(pred, pred_strides, pred_dtype, nullptr, nullptr, &lists, grad, grad_strides, terms, N, S,
                                 B, C, lambda_coord, lambda_noobj, inv_batch_size, coord_mode, workspace,
                                 workspace_bytes, 3 | (from_logits ? 4 : 0), variant, s);

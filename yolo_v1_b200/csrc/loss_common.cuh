@@ -57,10 +57,14 @@ struct LossParams {
   // object-list targets (yolo1_loss_fwd_bwd_objects): the dense target tensor is never materialised.
   // cellobj[q] = index of the object that owns cell q (the last one that falls into it, as the reference encoder
   // resolves collisions) or -1; the target values of an object cell are recomputed from boxes / labels.
+  // list_mode 2 (contiguous streaming kernel): no map at all -- the kernel finds the owners itself from `offsets`
+  // (objects of image n are [offsets[n], offsets[n+1])) and reports objects outside the grid through `status`.
   int list_mode;
   const int32_t* cellobj;
   const float* boxes;
   const int32_t* labels;
+  const int64_t* offsets;
+  int32_t* status;
   float cs;  // fl32(1/S)
 };
 
@@ -358,8 +362,39 @@ __device__ __forceinline__ ListTarget2 list_target2(const LossParams& p, const O
 __device__ __forceinline__ ListTarget2 list_target2(const LossParams& p, int k) {
   return list_target2(p, fetch_object(p, k));
 }
+// The cell an object falls into, as the reference encoder computes it (utils/YOLODataLoader.py:218-222, Python
+// indexing for negative indices); false = outside the grid or label out of range (the reference raises IndexError).
+__device__ __forceinline__ bool object_cell(const LossParams& p, const float4& box, int label, int& cell) {
+  float fi, fj, d;
+  encode_axis(box.x, p.cs, fi, d);
+  encode_axis(box.y, p.cs, fj, d);
+  int col = (int)fi, row = (int)fj;
+  const int S = p.S;
+  if (col < -S || col >= S || row < -S || row >= S || label < -p.C || label >= p.C) return false;
+  if (col < 0) col += S;
+  if (row < 0) row += S;
+  cell = row * S + col;
+  return true;
+}
+// list_mode 2, one cell at a time (ragged tail, the last CTA's fix-up): the last object of the cell's image that
+// falls into it, or -1
+__device__ __forceinline__ int owner_direct(const LossParams& p, int64_t q) {
+  const int SS = p.S * p.S;
+  const int64_t n = q / SS;
+  const int c = (int)(q - n * SS);
+  int owner = -1;
+  for (int64_t k = __ldg(p.offsets + n), hi = __ldg(p.offsets + n + 1); k < hi; ++k) {
+    int cell;
+    if (object_cell(p, __ldg(reinterpret_cast<const float4*>(p.boxes + 4 * k)), __ldg(p.labels + k), cell)) {
+      if (cell == c) owner = (int)k;
+    } else {
+      atomicExch(p.status, 1);
+    }
+  }
+  return owner;
+}
 __device__ __forceinline__ ListTargetS list_targetS(const LossParams& p, int64_t q) {
-  const ListTarget2 a = list_target2(p, p.cellobj[q]);
+  const ListTarget2 a = list_target2(p, p.list_mode == 2 ? owner_direct(p, q) : p.cellobj[q]);
   ListTargetS t;
   t.v[0] = a.dx, t.v[1] = a.dy, t.v[2] = a.w, t.v[3] = a.h, t.label = a.label, t.B = p.B, t.obj = a.obj;
   return t;
