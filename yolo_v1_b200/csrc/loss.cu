@@ -105,41 +105,48 @@ __global__ void __launch_bounds__(kGenericThreads) loss_generic_kernel(const __g
   block_epilogue<E, HAS_GRAD, false>(sums, m1, m2, p);  // no bulk stores in flight here
 }
 
-// object lists -> cell ownership map (yolo1_loss_fwd_bwd_objects): one thread per image walks its objects in input
-// order and records, per cell, the LAST object that falls into it (the reference encoder resets the cell before
-// each write, utils/YOLODataLoader.py:220); cells without object hold -1.  4 bytes per cell instead of a 120-byte
-// dense target row.
+// object lists -> cell ownership map (yolo1_loss_fwd_bwd_objects): per cell the LAST object of its image that falls
+// into it (the reference encoder resets the cell before each write, utils/YOLODataLoader.py:220); cells without
+// object hold -1.  4 bytes per cell instead of a 120-byte dense target row.
 __global__ void __launch_bounds__(256) object_cells_kernel(const float* __restrict__ boxes,
                                                            const int32_t* __restrict__ labels,
                                                            const int64_t* __restrict__ offsets, int64_t N, int S, int C,
                                                            float cs, int G, int32_t* __restrict__ cellobj,
                                                            int32_t* __restrict__ status) {
-  // A CTA builds the map of G whole images in shared memory (all -1, then thread i walks image i's objects in input
-  // order) and writes it out with coalesced 16-byte stores: one launch, every map byte written once -- no memset of
-  // the map beforehand, no scattered 4-byte global stores.
+  // A CTA builds the map of G whole images in shared memory and writes it out with coalesced 16-byte stores: one
+  // launch, every map byte written once -- no memset of the map beforehand, no scattered 4-byte global stores.
+  // One thread per OBJECT of those images (round 1: one thread per image walking its list -- three dependent trips
+  // to memory per object, 20 busy threads per CTA): the images' offsets go to shared memory first, then every object
+  // is one independent load; its image is the last one whose offset is <= its index (binary search over G + 1
+  // entries), and "the last object wins" is an atomicMax on the object index.
   extern __shared__ __align__(16) int32_t own[];
   const int SS = S * S;
   const int64_t g0 = (int64_t)blockIdx.x * G;
   const int n_img = (int)((N - g0 < G) ? N - g0 : G);
   const int total = n_img * SS;
+  int64_t* offs = reinterpret_cast<int64_t*>(own + (size_t)G * SS);   // G * SS * 4 is a multiple of 16 (host)
+  for (int t = threadIdx.x; t <= n_img; t += blockDim.x) offs[t] = __ldg(offsets + g0 + t);
   for (int t = threadIdx.x; t < total; t += blockDim.x) own[t] = -1;
   __syncthreads();
-  if ((int)threadIdx.x < n_img) {
-    const int64_t n = g0 + threadIdx.x;
-    for (int64_t k = offsets[n]; k < offsets[n + 1]; ++k) {
-      float fi, fj, d;
-      encode_axis(boxes[4 * k], cs, fi, d);
-      encode_axis(boxes[4 * k + 1], cs, fj, d);
-      int col = (int)fi, row = (int)fj;
-      const int lab = labels[k];
-      if (col < -S || col >= S || row < -S || row >= S || lab < -C || lab >= C) {  // reference: IndexError
-        atomicExch(status, 1);
-        continue;
-      }
-      if (col < 0) col += S;  // Python indexing
-      if (row < 0) row += S;
-      own[threadIdx.x * SS + row * S + col] = (int32_t)k;
+  for (int64_t k = offs[0] + threadIdx.x, hi = offs[n_img]; k < hi; k += blockDim.x) {
+    const float4 box = __ldg(reinterpret_cast<const float4*>(boxes) + k);
+    const int lab = __ldg(labels + k);
+    int a = 0, b = n_img;   // offs[a] <= k < offs[b]
+    while (b - a > 1) {
+      const int m = (a + b) >> 1;
+      if (offs[m] <= k) a = m; else b = m;
     }
+    float fi, fj, d;
+    encode_axis(box.x, cs, fi, d);
+    encode_axis(box.y, cs, fj, d);
+    int col = (int)fi, row = (int)fj;
+    if (col < -S || col >= S || row < -S || row >= S || lab < -C || lab >= C) {  // reference: IndexError
+      atomicExch(status, 1);
+      continue;
+    }
+    if (col < 0) col += S;  // Python indexing
+    if (row < 0) row += S;
+    atomicMax(&own[a * SS + row * S + col], (int32_t)k);
   }
   __syncthreads();
   int32_t* dst = cellobj + g0 * SS;   // 16-byte aligned: G * S * S is a multiple of 4 (host)
@@ -392,7 +399,7 @@ int yolo1_loss_fwd_bwd_objects_ex(const void* pred, const int64_t pred_strides[4
   if (cells > 0) {
     int G = 4096 / (S * S);   // ~16 KB of map per CTA
     G = G < 4 ? 4 : (G > 256 ? 256 : (G & ~3));   // a multiple of 4 images keeps every CTA's slice 16-byte aligned
-    const size_t smem = (size_t)G * S * S * sizeof(int32_t);
+    const size_t smem = (size_t)G * S * S * sizeof(int32_t) + (size_t)(G + 1) * sizeof(int64_t);
     if (smem > 200 * 1024) return YOLO1_ERR_UNSUPPORTED;
     static KernelPrep prep;
     if (int rc = prepare_kernel(prep, object_cells_kernel, 256, smem, false, nullptr, nullptr)) return rc;
